@@ -1,0 +1,715 @@
+// aec.cu - C-ABI host side of libaec_b200.so (see include/aec.h).
+//
+// Owns device memory, turns the reference's layer chain (src/models/event_numpy.py:53-73) into a
+// static launch schedule and issues the kernels of aec_kernels.cuh.  No torch types, no CPU
+// fallback: every compute entry point launches sm_100a kernels or fails.
+#include "../../include/aec.h"
+#include "aec_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace aec;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(AEC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static inline long long pad4(long long v) { return (v + 3) & ~3LL; }
+
+struct HostLayer {
+    int type = 0;
+    int C = 0, H = 0, W = 0, Ww = 0;
+    int Cin = 0, Hin = 0, Win = 0;
+    int kh = 0, kw = 0, stride = 1, pad_t = 0, pad_l = 0;
+    float alpha = 0.f;
+    int K = 0, Kpad = 0, Npad = 0, BN = 0;
+    long long fstride = 0;      // conv: floats per stream; pool: idx bytes per stream
+    std::vector<float> h_w, h_b;   // padded host copies until finalize
+    float *F = nullptr, *A = nullptr, *initF = nullptr;
+    uint8_t *idx = nullptr, *initIdx = nullptr;
+    uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr;
+    float *wgt = nullptr, *bias = nullptr;
+};
+
+struct aec_net {
+    int device = 0, S = 0, H = 0, W = 0;
+    double leak = 0;
+    int max_events = 2048, hash_slots = 4096;
+    bool finalized = false;
+    std::vector<HostLayer> L;
+    std::vector<void *> allocs;
+    size_t dev_bytes = 0, per_stream_bytes = 0;
+    double *surface = nullptr, *delta = nullptr;
+    int *prev_ts = nullptr;
+    uint8_t *active = nullptr, *mask = nullptr;
+    uint32_t *sites = nullptr;
+    int *counts = nullptr, *err_flag = nullptr;
+    unsigned long long *accum = nullptr;
+    float *head = nullptr;
+    size_t head_per_stream = 0;
+    int32_t *ev_dev = nullptr, *off_dev = nullptr;
+    size_t ev_cap = 0;
+    int num_sms = 148;
+    int sweep_chunks = 0;
+    SweepParams sweep_all;
+    unsigned long long launches = 0, steps = 0;
+    int conv_eval_blocks[4] = {0, 0, 0, 0};
+    float *view = nullptr;      // 4 x max(H*W*C) scratch for aec_net_read_view
+    size_t view_elems = 0;
+};
+
+template <typename T>
+static int dev_alloc(aec_net *n, T **out, size_t count, bool per_stream)
+{
+    void *p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(AEC_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return fail(AEC_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    n->allocs.push_back(p);
+    n->dev_bytes += bytes;
+    if (per_stream) n->per_stream_bytes += bytes / (size_t)n->S;
+    *out = static_cast<T *>(p);
+    return AEC_OK;
+}
+
+extern "C" const char *aec_last_error(void) { return g_err.c_str(); }
+extern "C" int aec_version(void) { return 1000; }
+
+extern "C" int aec_net_create(aec_net **out, int device, int n_streams, int height, int width, double leak,
+                              int max_events_per_step)
+{
+    if (!out) return fail(AEC_EINVAL, "out is NULL");
+    if (n_streams < 1 || n_streams > 65535) return fail(AEC_EINVAL, "n_streams must be in [1, 65535], got %d", n_streams);
+    if (height < 1 || width < 1) return fail(AEC_EINVAL, "bad surface size %dx%d", height, width);
+    if ((long long)n_streams * height * width >= (1LL << 32))
+        return fail(AEC_EINVAL, "n_streams*H*W must be < 2^32 (work-list entries are 32-bit)");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(AEC_EINVAL, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    aec_net *n = new aec_net();
+    n->device = device;
+    n->S = n_streams;
+    n->H = height;
+    n->W = width;
+    n->leak = leak;
+    if (max_events_per_step > 0) n->max_events = max_events_per_step;
+    int slots = 64;
+    while (slots < 2 * n->max_events) slots <<= 1;
+    n->hash_slots = slots;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    n->num_sms = prop.multiProcessorCount;
+    HostLayer l0;
+    l0.type = AEC_LAYER_INTEGRATION;
+    l0.C = 1;
+    l0.H = height;
+    l0.W = width;
+    l0.Ww = (width + 31) / 32;
+    n->L.push_back(l0);
+    *out = n;
+    return AEC_OK;
+}
+
+static void same_pad(int size, int k, int stride, int *before)
+{
+    int total = (size % stride == 0) ? (k - stride > 0 ? k - stride : 0) : (k - size % stride > 0 ? k - size % stride : 0);
+    *before = total / 2;
+}
+
+extern "C" int aec_net_add_conv(aec_net *n, int k_h, int k_w, int c_in, int c_out, const float *kernel_hwio,
+                                const float *bias, int stride, float alpha, int padding)
+{
+    if (!n || n->finalized) return fail(AEC_ESTATE, "add_conv after finalize (or NULL net)");
+    if (stride != 1) return fail(AEC_EINVAL, "only stride 1 convolutions are supported (event_numpy.py:64 always passes 1)");
+    if (k_h < 1 || k_w < 1 || k_h > 31 || k_w > 31) return fail(AEC_EINVAL, "kernel size %dx%d unsupported", k_h, k_w);
+    if (!kernel_hwio || !bias) return fail(AEC_EINVAL, "kernel/bias is NULL");
+    if ((int)n->L.size() >= 31) return fail(AEC_EINVAL, "too many layers");
+    const HostLayer &p = n->L.back();
+    if (c_in != p.C) return fail(AEC_EINVAL, "conv expects %d input channels but previous layer has %d", c_in, p.C);
+    int nconv = 0;
+    for (auto &l : n->L) nconv += l.type == AEC_LAYER_CONV;
+    if (nconv >= kMaxConv) return fail(AEC_EINVAL, "too many conv layers");
+    HostLayer l;
+    l.type = AEC_LAYER_CONV;
+    l.Cin = p.C; l.Hin = p.H; l.Win = p.W;
+    l.kh = k_h; l.kw = k_w; l.stride = 1; l.alpha = alpha;
+    if (padding == AEC_PAD_SAME) {            // conv2d.py:38-54
+        l.H = p.H; l.W = p.W;
+        same_pad(p.H, k_h, 1, &l.pad_t);
+        same_pad(p.W, k_w, 1, &l.pad_l);
+    } else if (padding == AEC_PAD_VALID) {    // conv2d.py:34-37
+        l.H = p.H - k_h + 1; l.W = p.W - k_w + 1;
+        if (l.H < 1 || l.W < 1) return fail(AEC_EINVAL, "VALID conv larger than its input");
+    } else {
+        return fail(AEC_EINVAL, "'padding' must be either 'SAME' or 'VALID'");
+    }
+    l.C = c_out;
+    l.Ww = (l.W + 31) / 32;
+    l.K = k_h * k_w * c_in;
+    l.BN = c_out <= 16 ? 16 : c_out <= 32 ? 32 : c_out <= 64 ? 64 : 128;
+    l.Npad = (c_out + l.BN - 1) / l.BN * l.BN;
+    l.Kpad = (l.K + 15) / 16 * 16;
+    l.fstride = pad4((long long)l.H * l.W * l.C);
+    l.h_w.assign((size_t)l.Kpad * l.Npad, 0.f);
+    l.h_b.assign((size_t)l.Npad, 0.f);
+    for (int k = 0; k < l.K; ++k)          // HWIO flattened is already [k = (ky,kx,ci)][co]
+        for (int c = 0; c < c_out; ++c) l.h_w[(size_t)k * l.Npad + c] = kernel_hwio[(size_t)k * c_out + c];
+    for (int c = 0; c < c_out; ++c) l.h_b[c] = bias[c];
+    n->L.push_back(std::move(l));
+    return (int)n->L.size() - 1;
+}
+
+extern "C" int aec_net_add_pool(aec_net *n, int k_h, int k_w, int stride)
+{
+    if (!n || n->finalized) return fail(AEC_ESTATE, "add_pool after finalize (or NULL net)");
+    if ((int)n->L.size() >= 31) return fail(AEC_EINVAL, "too many layers");
+    const HostLayer &p = n->L.back();
+    if (p.type != AEC_LAYER_CONV) return fail(AEC_EINVAL, "a pool layer must follow a conv layer");
+    if (!(stride == k_h && stride == k_w))   // cutils.pyx:88-89
+        return fail(AEC_EINVAL, "This method only support stride equal to 1 or to the kernel's dimensions.");
+    if (k_h * k_w > 255) return fail(AEC_EINVAL, "pool window too large");
+    if (p.H % stride || p.W % stride)
+        return fail(AEC_EINVAL, "pool input %dx%d is not a multiple of the stride %d (the reference indexes out of range, SURVEY Q6)",
+                    p.H, p.W, stride);
+    HostLayer l;
+    l.type = AEC_LAYER_POOL;
+    l.Cin = p.C; l.Hin = p.H; l.Win = p.W;
+    l.kh = k_h; l.kw = k_w; l.stride = stride;
+    l.C = p.C;
+    l.H = (p.H - k_h) / stride + 1;    // maxpool.py:27-28
+    l.W = (p.W - k_w) / stride + 1;
+    l.Ww = (l.W + 31) / 32;
+    l.fstride = pad4((long long)l.H * l.W * l.C);
+    n->L.push_back(std::move(l));
+    return (int)n->L.size() - 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+static Src make_src(const aec_net *n, int li)
+{
+    const HostLayer &l = n->L[li];
+    Src q;
+    memset(&q, 0, sizeof q);
+    q.C = l.C; q.H = l.H; q.W = l.W;
+    if (l.type == AEC_LAYER_INTEGRATION) {
+        q.kind = 0;
+        q.S = n->surface;
+        q.sstride = (long long)l.H * l.W;
+    } else if (l.type == AEC_LAYER_CONV) {
+        q.kind = 1;
+        q.F = l.F; q.A = l.A; q.fstride = l.fstride; q.alpha = l.alpha;
+    } else {
+        const HostLayer &c = n->L[li - 1];
+        q.kind = 2;
+        q.F = c.F; q.A = c.A; q.fstride = c.fstride; q.alpha = c.alpha; q.cW = c.W;
+        q.idx = l.idx; q.istride = l.fstride; q.pkw = l.kw; q.pstride = l.stride;
+    }
+    return q;
+}
+
+static int launch_check(aec_net *n, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AEC_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    n->launches++;
+    return AEC_OK;
+}
+
+static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cudaStream_t st)
+{
+    const HostLayer &l = n->L[0];
+    IntegrateParams p;
+    p.surface = n->surface; p.prev_ts = n->prev_ts; p.delta = n->delta; p.active = n->active;
+    p.front = l.front; p.events = ev; p.offsets = off; p.layer_counts = n->counts; p.err_flag = n->err_flag;
+    p.n_layers = (int)n->L.size();
+    p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.leak = n->leak; p.max_events = n->max_events; p.hash_slots = n->hash_slots;
+    const size_t smem = (size_t)n->hash_slots * 8 + (size_t)l.H * l.Ww * 4;
+    k_integrate<<<n->S, kThreads, smem, st>>>(p);
+    return launch_check(n, "k_integrate");
+}
+
+static void fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0)
+{
+    o.F = l.F; o.A = l.A; o.signchg = l.signchg; o.fstride = l.fstride;
+    o.n4 = (int)(l.fstride / 4); o.chunk0 = chunk0;
+    o.C = l.C; o.W = l.W; o.Ww = l.Ww; o.HWw = l.H * l.Ww;
+}
+
+static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
+{
+    if (only_layer < 0) {
+        if (n->sweep_all.n_layers == 0) return AEC_OK;
+        dim3 grid(n->sweep_chunks, n->S);
+        k_leak_sweep<<<grid, kThreads, 0, st>>>(n->sweep_all);
+        return launch_check(n, "k_leak_sweep");
+    }
+    SweepParams p;
+    memset(&p, 0, sizeof p);
+    fill_sweep_layer(n->L[only_layer], p.L[0], 0);
+    p.n_layers = 1; p.delta = n->delta; p.active = n->active;
+    dim3 grid((p.L[0].n4 + kSweepChunk - 1) / kSweepChunk, n->S);
+    k_leak_sweep<<<grid, kThreads, 0, st>>>(p);
+    return launch_check(n, "k_leak_sweep");
+}
+
+static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
+{
+    HostLayer &l = n->L[li];
+    ConvEvalParams p;
+    p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
+    p.src = make_src(n, li - 1);
+    p.wgt = l.wgt; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.Kpad = l.Kpad; p.Npad = l.Npad;
+    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+    switch (l.BN) {
+    case 16: k_conv_eval<16, 2, 4, 16><<<n->conv_eval_blocks[0], kThreads, 0, st>>>(p); break;
+    case 32: k_conv_eval<32, 4, 4, 16><<<n->conv_eval_blocks[1], kThreads, 0, st>>>(p); break;
+    case 64: k_conv_eval<64, 4, 8, 16><<<n->conv_eval_blocks[2], kThreads, 0, st>>>(p); break;
+    default: k_conv_eval<128, 8, 8, 16><<<n->conv_eval_blocks[3], kThreads, 0, st>>>(p); break;
+    }
+    return launch_check(n, "k_conv_eval");
+}
+
+static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
+{
+    HostLayer &l = n->L[li];
+    const HostLayer &c = n->L[li - 1];
+    PoolEvalParams p;
+    p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
+    p.F = c.F; p.A = c.A; p.fstride = c.fstride; p.alpha = c.alpha; p.cW = c.W;
+    p.idx = l.idx; p.istride = l.fstride; p.flags = l.flags;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
+    k_pool_eval<<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    return launch_check(n, "k_pool_eval");
+}
+
+static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
+{
+    HostLayer &l = n->L[li];
+    const HostLayer &pv = n->L[li - 1];
+    int rc;
+    if (l.type == AEC_LAYER_CONV) {
+        if (with_sweep && (rc = run_sweep(n, li, st))) return rc;
+        ConvFrontParams p;
+        p.prev_front = pv.front; p.front = l.front; p.signchg = l.signchg; p.active = n->active;
+        p.sites = n->sites; p.counter = n->counts + li;
+        p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
+        p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+        const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4;
+        k_conv_frontier<<<n->S, kThreads, smem, st>>>(p);
+        if ((rc = launch_check(n, "k_conv_frontier"))) return rc;
+        return run_conv_eval(n, li, st);
+    }
+    PoolFrontParams p;
+    p.prev_front = pv.front; p.front = l.front; p.flags = l.flags; p.active = n->active;
+    p.sites = n->sites; p.counter = n->counts + li;
+    p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
+    p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
+    const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4;
+    k_pool_frontier<<<n->S, kThreads, smem, st>>>(p);
+    if ((rc = launch_check(n, "k_pool_frontier"))) return rc;
+    return run_pool_eval(n, li, st);
+}
+
+static int run_head(aec_net *n, cudaStream_t st)
+{
+    HeadParams p;
+    p.src = make_src(n, (int)n->L.size() - 1);
+    p.out = n->head;
+    p.S = n->S;
+    long long total = (long long)n->head_per_stream * n->S;
+    int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
+    k_head<<<blocks, kThreads, 0, st>>>(p);
+    return launch_check(n, "k_head");
+}
+
+static int broadcast(aec_net *n, void *dst, const void *src, long long bytes_per_stream, long long stride_bytes,
+                     const uint8_t *mask, cudaStream_t st)
+{
+    const long long words = bytes_per_stream / 4;
+    int bx = (int)std::min<long long>((words + kThreads - 1) / kThreads, 64);
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, n->S);
+    k_broadcast_words<<<grid, kThreads, 0, st>>>((uint32_t *)dst, (const uint32_t *)src, words, stride_bytes / 4, mask);
+    return launch_check(n, "k_broadcast_words");
+}
+
+static int reset_streams(aec_net *n, const uint8_t *mask_dev, cudaStream_t st)
+{
+    int rc;
+    const HostLayer &l0 = n->L[0];
+    if ((rc = broadcast(n, n->surface, nullptr, (long long)l0.H * l0.W * 8, (long long)l0.H * l0.W * 8, mask_dev, st))) return rc;
+    k_reset_scalars<<<(n->S + kThreads - 1) / kThreads, kThreads, 0, st>>>(n->prev_ts, n->delta, n->active, mask_dev, n->S);
+    if ((rc = launch_check(n, "k_reset_scalars"))) return rc;
+    for (auto &l : n->L) {
+        const long long bm = (long long)l.H * l.Ww * 4;
+        if ((rc = broadcast(n, l.front, nullptr, bm, bm, mask_dev, st))) return rc;
+        if (l.type == AEC_LAYER_CONV) {
+            if ((rc = broadcast(n, l.F, l.initF, l.fstride * 4, l.fstride * 4, mask_dev, st))) return rc;
+            if ((rc = broadcast(n, l.A, nullptr, l.fstride * 4, l.fstride * 4, mask_dev, st))) return rc;
+            if ((rc = broadcast(n, l.signchg, nullptr, bm, bm, mask_dev, st))) return rc;
+        } else if (l.type == AEC_LAYER_POOL) {
+            if ((rc = broadcast(n, l.idx, l.initIdx, l.fstride, l.fstride, mask_dev, st))) return rc;
+            if ((rc = broadcast(n, l.flags, nullptr, bm, bm, mask_dev, st))) return rc;
+        }
+    }
+    return AEC_OK;
+}
+
+extern "C" int aec_net_finalize(aec_net *n)
+{
+    if (!n || n->finalized) return fail(AEC_ESTATE, "finalize called twice (or NULL net)");
+    if (n->L.size() < 2) return fail(AEC_EINVAL, "network has no layers after the integration surface");
+    CU(cudaSetDevice(n->device));
+    int rc;
+    const size_t S = (size_t)n->S;
+    size_t maxHW = 0;
+    if ((rc = dev_alloc(n, &n->surface, S * n->H * n->W, true))) return rc;
+    if ((rc = dev_alloc(n, &n->delta, S, true))) return rc;
+    if ((rc = dev_alloc(n, &n->prev_ts, S, true))) return rc;
+    if ((rc = dev_alloc(n, &n->active, S, true))) return rc;
+    if ((rc = dev_alloc(n, &n->mask, S, true))) return rc;
+    for (auto &l : n->L) {
+        const size_t bm = (size_t)l.H * l.Ww;
+        if ((rc = dev_alloc(n, &l.front, S * bm, true))) return rc;
+        if (l.type == AEC_LAYER_CONV) {
+            if ((rc = dev_alloc(n, &l.F, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc(n, &l.A, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc(n, &l.signchg, S * bm, true))) return rc;
+            if ((rc = dev_alloc(n, &l.initF, (size_t)l.fstride, false))) return rc;
+            if ((rc = dev_alloc(n, &l.wgt, l.h_w.size(), false))) return rc;
+            if ((rc = dev_alloc(n, &l.bias, l.h_b.size(), false))) return rc;
+            CU(cudaMemcpy(l.wgt, l.h_w.data(), l.h_w.size() * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(l.bias, l.h_b.data(), l.h_b.size() * 4, cudaMemcpyHostToDevice));
+            l.h_w.clear(); l.h_w.shrink_to_fit();
+        } else if (l.type == AEC_LAYER_POOL) {
+            if ((rc = dev_alloc(n, &l.idx, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc(n, &l.flags, S * bm, true))) return rc;
+            if ((rc = dev_alloc(n, &l.initIdx, (size_t)l.fstride, false))) return rc;
+        }
+        if (l.type != AEC_LAYER_INTEGRATION) maxHW = std::max(maxHW, (size_t)l.H * l.W);
+    }
+    if ((rc = dev_alloc(n, &n->sites, S * maxHW, true))) return rc;
+    for (auto &l : n->L)
+        if (l.type != AEC_LAYER_INTEGRATION) n->view_elems = std::max(n->view_elems, (size_t)l.H * l.W * l.C);
+    if ((rc = dev_alloc(n, &n->view, 4 * n->view_elems, false))) return rc;
+    if ((rc = dev_alloc(n, &n->counts, 32, false))) return rc;
+    if ((rc = dev_alloc(n, &n->accum, 32, false))) return rc;
+    if ((rc = dev_alloc(n, &n->err_flag, 1, false))) return rc;
+    if ((rc = dev_alloc(n, &n->off_dev, S + 1, false))) return rc;
+    const HostLayer &last = n->L.back();
+    n->head_per_stream = (size_t)last.H * last.W * last.C;
+    if ((rc = dev_alloc(n, &n->head, S * n->head_per_stream, true))) return rc;
+
+    // leak-sweep table over all conv layers
+    memset(&n->sweep_all, 0, sizeof n->sweep_all);
+    int chunk0 = 0, nc = 0;
+    for (auto &l : n->L)
+        if (l.type == AEC_LAYER_CONV) {
+            fill_sweep_layer(l, n->sweep_all.L[nc], chunk0);
+            chunk0 += (n->sweep_all.L[nc].n4 + kSweepChunk - 1) / kSweepChunk;
+            ++nc;
+        }
+    n->sweep_all.n_layers = nc;
+    n->sweep_all.delta = n->delta;
+    n->sweep_all.active = n->active;
+    n->sweep_chunks = chunk0;
+
+    // shared-memory opt-ins and persistent grid sizes
+    {
+        size_t need = (size_t)n->hash_slots * 8 + (size_t)n->L[0].H * n->L[0].Ww * 4;
+        if (need > 200 * 1024) return fail(AEC_EINVAL, "max_events_per_step/surface too large for the surface kernel's shared memory");
+        CU(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(need, 48 * 1024)));
+        size_t fc = 0, fp = 0;
+        for (size_t i = 1; i < n->L.size(); ++i) {
+            const HostLayer &l = n->L[i], &pv = n->L[i - 1];
+            if (l.type == AEC_LAYER_CONV) fc = std::max(fc, ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4);
+            else fp = std::max(fp, ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4);
+        }
+        if (fc > 200 * 1024 || fp > 200 * 1024) return fail(AEC_EINVAL, "frame too large for the frontier kernels' shared memory");
+        CU(cudaFuncSetAttribute(k_conv_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fc, 48 * 1024)));
+        CU(cudaFuncSetAttribute(k_pool_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fp, 48 * 1024)));
+        int b = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));
+        n->conv_eval_blocks[0] = std::max(1, b) * n->num_sms;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<32, 4, 4, 16>, kThreads, 0));
+        n->conv_eval_blocks[1] = std::max(1, b) * n->num_sms;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<64, 4, 8, 16>, kThreads, 0));
+        n->conv_eval_blocks[2] = std::max(1, b) * n->num_sms;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<128, 8, 8, 16>, kThreads, 0));
+        n->conv_eval_blocks[3] = std::max(1, b) * n->num_sms;
+    }
+
+    // initial state = the chain evaluated on the all-zero surface (conv2d.py:59-63, maxpool.py:31-36),
+    // computed once on stream 0 with "every site" work lists, then broadcast by reset.
+    cudaStream_t st = 0;
+    for (size_t li = 1; li < n->L.size(); ++li) {
+        HostLayer &l = n->L[li];
+        const int HW = l.H * l.W;
+        k_all_sites<<<(HW + kThreads - 1) / kThreads, kThreads, 0, st>>>(n->sites, n->counts + li, HW);
+        if ((rc = launch_check(n, "k_all_sites"))) return rc;
+        if (l.type == AEC_LAYER_CONV) {
+            if ((rc = run_conv_eval(n, (int)li, st))) return rc;
+            CU(cudaMemcpyAsync(l.initF, l.F, (size_t)l.fstride * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemsetAsync(l.A, 0, (size_t)l.fstride * 4, st));   // `_init_conv_actfn = zeros` (conv2d.py:62)
+        } else {
+            if ((rc = run_pool_eval(n, (int)li, st))) return rc;
+            CU(cudaMemcpyAsync(l.initIdx, l.idx, (size_t)l.fstride, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemsetAsync(l.flags, 0, (size_t)l.H * l.Ww * 4, st));
+        }
+    }
+    CU(cudaMemsetAsync(n->accum, 0, 32 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(n->counts, 0, 32 * sizeof(int), st));
+    if ((rc = reset_streams(n, nullptr, st))) return rc;
+    CU(cudaStreamSynchronize(st));
+    n->finalized = true;
+    n->steps = 0;
+    return AEC_OK;
+}
+
+extern "C" void aec_net_destroy(aec_net *n)
+{
+    if (!n) return;
+    cudaSetDevice(n->device);
+    cudaDeviceSynchronize();
+    for (void *p : n->allocs) cudaFree(p);
+    if (n->ev_dev) cudaFree(n->ev_dev);
+    delete n;
+}
+
+extern "C" int aec_net_num_layers(const aec_net *n) { return n ? (int)n->L.size() : 0; }
+extern "C" int aec_net_num_streams(const aec_net *n) { return n ? n->S : 0; }
+extern "C" size_t aec_net_state_bytes_per_stream(const aec_net *n) { return n ? n->per_stream_bytes : 0; }
+extern "C" size_t aec_net_device_bytes(const aec_net *n) { return n ? n->dev_bytes : 0; }
+extern "C" unsigned long long aec_net_launch_count(const aec_net *n) { return n ? n->launches : 0; }
+
+extern "C" int aec_net_layer_info(const aec_net *n, int layer, aec_layer_info *info)
+{
+    if (!n || !info || layer < 0 || layer >= (int)n->L.size()) return fail(AEC_EINVAL, "bad layer index %d", layer);
+    const HostLayer &l = n->L[layer];
+    info->type = l.type; info->channels = l.C; info->height = l.H; info->width = l.W;
+    info->k_h = l.kh; info->k_w = l.kw; info->stride = l.stride; info->pad_top = l.pad_t; info->pad_left = l.pad_l;
+    info->in_channels = l.Cin; info->frontier_words_per_row = l.Ww;
+    return AEC_OK;
+}
+
+#define NEED_FINAL(n)                                                                   \
+    do {                                                                                \
+        if (!(n) || !(n)->finalized) return fail(AEC_ESTATE, "network is not finalized"); \
+        CU(cudaSetDevice((n)->device));                                                 \
+    } while (0)
+
+extern "C" int aec_net_reset(aec_net *n, const uint8_t *stream_mask, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint8_t *m = nullptr;
+    if (stream_mask) {
+        CU(cudaMemcpyAsync(n->mask, stream_mask, (size_t)n->S, cudaMemcpyHostToDevice, st));
+        m = n->mask;
+    }
+    return reset_streams(n, m, st);
+}
+
+extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t *off, int total, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    (void)total;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    if ((rc = run_integrate(n, ev, off, st))) return rc;
+    if ((rc = run_sweep(n, -1, st))) return rc;
+    for (int li = 1; li < (int)n->L.size(); ++li)
+        if ((rc = run_layer(n, li, false, st))) return rc;
+    if ((rc = run_head(n, st))) return rc;
+    n->steps++;
+    return AEC_OK;
+}
+
+static int upload_events(aec_net *n, const int32_t *ev, const int32_t *off, int total, cudaStream_t st)
+{
+    if (total < 0 || !off || (total > 0 && !ev)) return fail(AEC_EINVAL, "bad event buffers");
+    if ((size_t)total > n->ev_cap) {
+        CU(cudaStreamSynchronize(st));
+        if (n->ev_dev) { CU(cudaFree(n->ev_dev)); n->ev_dev = nullptr; }
+        size_t cap = std::max<size_t>((size_t)total * 3 / 2, 1024);
+        CU(cudaMalloc(&n->ev_dev, cap * 3 * sizeof(int32_t)));
+        n->ev_cap = cap;
+    }
+    if (total > 0) CU(cudaMemcpyAsync(n->ev_dev, ev, (size_t)total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(n->off_dev, off, ((size_t)n->S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return AEC_OK;
+}
+
+static int check_err_flag(aec_net *n, cudaStream_t st)
+{
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, n->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag) {
+        CU(cudaMemsetAsync(n->err_flag, 0, sizeof(int), st));
+        return fail(AEC_EEVENTS, "%s%s", (flag & 1) ? "event coordinates out of range (event skipped). " : "",
+                    (flag & 2) ? "a stream exceeded max_events_per_step (stream skipped)." : "");
+    }
+    return AEC_OK;
+}
+
+extern "C" int aec_net_step_host(aec_net *n, const int32_t *ev, const int32_t *off, int total, float *head_out, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    if ((rc = upload_events(n, ev, off, total, st))) return rc;
+    if ((rc = aec_net_step_device(n, n->ev_dev, n->off_dev, total, cuda_stream))) return rc;
+    if (head_out)
+        CU(cudaMemcpyAsync(head_out, n->head, (size_t)n->S * n->head_per_stream * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return check_err_flag(n, st);
+}
+
+extern "C" const float *aec_net_head_device(const aec_net *n) { return n ? n->head : nullptr; }
+extern "C" size_t aec_net_head_elems_per_stream(const aec_net *n) { return n ? n->head_per_stream : 0; }
+
+extern "C" int aec_net_begin_step(aec_net *n, const int32_t *ev, const int32_t *off, int total, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc;
+    if ((rc = upload_events(n, ev, off, total, st))) return rc;
+    if ((rc = run_integrate(n, n->ev_dev, n->off_dev, st))) return rc;
+    n->steps++;
+    return check_err_flag(n, st);
+}
+
+extern "C" int aec_net_layer_compute(aec_net *n, int layer, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    if (layer < 1 || layer >= (int)n->L.size()) return fail(AEC_EINVAL, "layer_compute: layer %d out of range", layer);
+    return run_layer(n, layer, true, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int aec_net_compute_head(aec_net *n, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    return run_head(n, (cudaStream_t)cuda_stream);
+}
+
+extern "C" long long aec_net_read_size(const aec_net *n, int layer, int what)
+{
+    if (!n || layer < 0 || layer >= (int)n->L.size()) return fail(AEC_EINVAL, "bad layer index %d", layer);
+    const HostLayer &l = n->L[layer];
+    const long long hwc = (long long)l.H * l.W * l.C, bm = (long long)l.H * l.Ww * 4;
+    switch (what) {
+    case AEC_READ_SURFACE: return l.type == AEC_LAYER_INTEGRATION ? hwc * 8 : fail(AEC_EINVAL, "layer %d has no surface", layer);
+    case AEC_READ_F: case AEC_READ_A: case AEC_READ_INIT_F:
+        return l.type == AEC_LAYER_CONV ? hwc * 4 : fail(AEC_EINVAL, "layer %d is not a conv layer", layer);
+    case AEC_READ_IDX: case AEC_READ_INIT_IDX:
+        return l.type == AEC_LAYER_POOL ? hwc : fail(AEC_EINVAL, "layer %d is not a pool layer", layer);
+    case AEC_READ_FLAGS: return l.type == AEC_LAYER_POOL ? bm : fail(AEC_EINVAL, "layer %d is not a pool layer", layer);
+    case AEC_READ_FRONTIER: return bm;
+    default: return fail(AEC_EINVAL, "unknown read selector %d", what);
+    }
+}
+
+extern "C" int aec_net_read(aec_net *n, int layer, int what, int stream, void *host_out, size_t bytes)
+{
+    NEED_FINAL(n);
+    if (stream < 0 || stream >= n->S) return fail(AEC_EINVAL, "stream %d out of range", stream);
+    const long long need = aec_net_read_size(n, layer, what);
+    if (need < 0) return (int)need;
+    if ((size_t)need != bytes) return fail(AEC_EINVAL, "read: buffer is %zu bytes, need %lld", bytes, need);
+    const HostLayer &l = n->L[layer];
+    const size_t s = (size_t)stream;
+    const void *src = nullptr;
+    switch (what) {
+    case AEC_READ_SURFACE: src = n->surface + s * l.H * l.W; break;
+    case AEC_READ_F: src = l.F + s * l.fstride; break;
+    case AEC_READ_A: src = l.A + s * l.fstride; break;
+    case AEC_READ_INIT_F: src = l.initF; break;
+    case AEC_READ_IDX: src = l.idx + s * l.fstride; break;
+    case AEC_READ_INIT_IDX: src = l.initIdx; break;
+    case AEC_READ_FLAGS: src = l.flags + s * l.H * l.Ww; break;
+    case AEC_READ_FRONTIER: src = l.front + s * l.H * l.Ww; break;
+    }
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
+    return AEC_OK;
+}
+
+extern "C" int aec_net_read_step_info(aec_net *n, double *delta_out, uint8_t *active_out)
+{
+    NEED_FINAL(n);
+    CU(cudaDeviceSynchronize());
+    if (delta_out) CU(cudaMemcpy(delta_out, n->delta, (size_t)n->S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (active_out) CU(cudaMemcpy(active_out, n->active, (size_t)n->S, cudaMemcpyDeviceToHost));
+    return AEC_OK;
+}
+
+extern "C" int aec_net_read_counters(aec_net *n, unsigned long long *sites, int n_layers, unsigned long long *steps, int reset)
+{
+    NEED_FINAL(n);
+    CU(cudaDeviceSynchronize());
+    unsigned long long tmp[32];
+    CU(cudaMemcpy(tmp, n->accum, sizeof tmp, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_layers && i < 32; ++i)
+        if (sites) sites[i] = i < (int)n->L.size() ? tmp[i] : 0ULL;
+    if (steps) *steps = n->steps;
+    if (reset) {
+        CU(cudaMemset(n->accum, 0, sizeof tmp));
+        n->steps = 0;
+    }
+    return AEC_OK;
+}
+
+extern "C" int aec_net_read_view(aec_net *n, int layer, int stream, float *surface, float *layer_actfn, float *conv_actfn,
+                                 float *featuremap)
+{
+    NEED_FINAL(n);
+    if (layer < 1 || layer >= (int)n->L.size()) return fail(AEC_EINVAL, "read_view: layer %d is not a conv/pool layer", layer);
+    if (stream < 0 || stream >= n->S) return fail(AEC_EINVAL, "stream %d out of range", stream);
+    const HostLayer &l = n->L[layer];
+    const size_t per = (size_t)l.H * l.W * l.C;
+    ViewParams p;
+    p.src = make_src(n, layer);
+    p.stream = stream;
+    p.surface = surface ? n->view : nullptr;
+    p.layer_actfn = layer_actfn ? n->view + n->view_elems : nullptr;
+    p.conv_actfn = conv_actfn ? n->view + 2 * n->view_elems : nullptr;
+    p.featuremap = featuremap ? n->view + 3 * n->view_elems : nullptr;
+    CU(cudaDeviceSynchronize());
+    int blocks = (int)std::min<size_t>((per + kThreads - 1) / kThreads, (size_t)n->num_sms * 8);
+    k_layer_view<<<blocks, kThreads>>>(p);
+    int rc = launch_check(n, "k_layer_view");
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    if (surface) CU(cudaMemcpy(surface, p.surface, per * 4, cudaMemcpyDeviceToHost));
+    if (layer_actfn) CU(cudaMemcpy(layer_actfn, p.layer_actfn, per * 4, cudaMemcpyDeviceToHost));
+    if (conv_actfn) CU(cudaMemcpy(conv_actfn, p.conv_actfn, per * 4, cudaMemcpyDeviceToHost));
+    if (featuremap) CU(cudaMemcpy(featuremap, p.featuremap, per * 4, cudaMemcpyDeviceToHost));
+    return AEC_OK;
+}

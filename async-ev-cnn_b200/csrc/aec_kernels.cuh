@@ -1,0 +1,843 @@
+// aec_kernels.cuh - sm_100a kernels of the event-driven EFCN hot path.
+//
+// Data layout in HBM (per network, S streams; the stream index is always outermost):
+//   surface   double [S][H*W]                     leaky integration surface (f64: SURVEY Q2)
+//   F_l, A_l  float  [S][pad4(H_l*W_l*C_l)]        conv pre-activation / leak-rate maps, CHANNEL-LAST
+//   idx_l     uint8  [S][Ho*Wo*C]                  pool argmax row (ky*kw+kx), channel-last
+//   flags_l   uint32 [S][Ho][ceil(Wo/32)]          pool sticky recompute bitmap
+//   front_l   uint32 [S][H_l][ceil(W_l/32)]        output-event ("frontier") bitmap of layer l
+//   signchg_l uint32 [S][H_l][ceil(W_l/32)]        conv sites whose sign flipped in the leak sweep
+//   sites     uint32 [S*max(H_l*W_l)]              gathered work list of the layer being updated:
+//                                                  entry = stream*H_l*W_l + y*W_l + x, streams batched
+//
+// Semantics follow the reference line by line (citations at each kernel); the work decomposition is
+// new: frontiers are bitmaps (dedup and ordering for free), the leak of ALL conv layers is one
+// vectorised sweep, and changed sites of all streams are gathered into one list per layer so the
+// re-evaluation runs as a dense gathered GEMM over (sites x {value,rate}) x k*k*Cin x Cout.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+namespace aec {
+
+constexpr int kThreads = 256;
+constexpr int kMaxConv = 24;
+
+// ---------------------------------------------------------------------------------------------
+// What a consumer sees of its previous layer: value V = surface*layer_actfn (layer.py:77-81) and
+// rate R = conv_actfn.  kind 0: integration (V=(float)S, R=[S>0]; integration.py:33-43),
+// kind 1: conv (V=F*slope, R=A*slope, slope = F>0 ? 1 : alpha; conv2d.py:83-94),
+// kind 2: pool over a conv (the same, read through the stored argmax; maxpool.py:42-79).
+// ---------------------------------------------------------------------------------------------
+struct Src {
+    int kind;
+    int C, H, W;            // shape of the previous layer's output map
+    const double *S;        // kind 0
+    long long sstride;
+    const float *F, *A;     // kind 1/2: the underlying conv maps
+    long long fstride;
+    float alpha;
+    int cW;                 // kind 2: width of the underlying conv map
+    const uint8_t *idx;     // kind 2
+    long long istride;
+    int pkw, pstride;       // kind 2: pool window width / stride
+};
+
+__device__ __forceinline__ float slope_of(float f, float alpha) { return f > 0.f ? 1.f : alpha; }
+
+__device__ __forceinline__ void src_fetch(const Src &q, int s, int y, int x, int c, float &v, float &r)
+{
+    if (q.kind == 0) {
+        const double sv = q.S[(long long)s * q.sstride + (long long)y * q.W + x];
+        v = __double2float_rn(sv);
+        r = sv > 0.0 ? 1.f : 0.f;
+        return;
+    }
+    long long off;
+    if (q.kind == 1) {
+        off = ((long long)y * q.W + x) * q.C + c;
+    } else {
+        const int i = q.idx[(long long)s * q.istride + ((long long)y * q.W + x) * q.C + c];
+        off = ((long long)(y * q.pstride + i / q.pkw) * q.cW + (x * q.pstride + i % q.pkw)) * q.C + c;
+    }
+    const float f = q.F[(long long)s * q.fstride + off];
+    const float a = q.A[(long long)s * q.fstride + off];
+    const float sl = slope_of(f, q.alpha);
+    v = __fmul_rn(f, sl);
+    r = __fmul_rn(a, sl);
+}
+
+// 4 consecutive channels (c % 4 == 0, C % 4 == 0).
+__device__ __forceinline__ void src_fetch4(const Src &q, int s, int y, int x, int c, float4 &v, float4 &r)
+{
+    if (q.kind == 1) {
+        const long long off = (long long)s * q.fstride + ((long long)y * q.W + x) * q.C + c;
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(q.F + off));
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(q.A + off));
+        float sl;
+        sl = slope_of(f.x, q.alpha); v.x = __fmul_rn(f.x, sl); r.x = __fmul_rn(a.x, sl);
+        sl = slope_of(f.y, q.alpha); v.y = __fmul_rn(f.y, sl); r.y = __fmul_rn(a.y, sl);
+        sl = slope_of(f.z, q.alpha); v.z = __fmul_rn(f.z, sl); r.z = __fmul_rn(a.z, sl);
+        sl = slope_of(f.w, q.alpha); v.w = __fmul_rn(f.w, sl); r.w = __fmul_rn(a.w, sl);
+    } else {
+        src_fetch(q, s, y, x, c + 0, v.x, r.x);
+        src_fetch(q, s, y, x, c + 1, v.y, r.y);
+        src_fetch(q, s, y, x, c + 2, v.z, r.z);
+        src_fetch(q, s, y, x, c + 3, v.w, r.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small block-level helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+
+// Exclusive prefix sum of one int per thread over the block (kThreads threads); returns the
+// exclusive prefix, writes the block total to *total.  `scratch` = 9 ints of shared memory.
+__device__ __forceinline__ int block_excl_scan(int v, int *scratch, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int incl = warp_incl_scan(v);
+    if (lane == 31) scratch[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < (kThreads / 32) ? scratch[lane] : 0;
+        const int wi = warp_incl_scan(w);
+        if (lane < (kThreads / 32)) scratch[lane] = wi - w;
+        if (lane == (kThreads / 32) - 1) scratch[8] = wi;
+    }
+    __syncthreads();
+    const int res = scratch[wid] + incl - v;
+    *total = scratch[8];
+    __syncthreads();
+    return res;
+}
+
+// Word w of a bitmap row shifted by d bit positions towards higher x (d may be negative).
+__device__ __forceinline__ uint32_t row_shift(const uint32_t *row, int nwords, int w, int d)
+{
+    if (d == 0) return row[w];
+    if (d > 0) {
+        const int ws = d >> 5, b = d & 31;
+        const int i = w - ws;
+        uint32_t lo = (i >= 0 && i < nwords) ? row[i] : 0u;
+        if (b == 0) return lo;
+        uint32_t prev = (i - 1 >= 0 && i - 1 < nwords) ? row[i - 1] : 0u;
+        return (lo << b) | (prev >> (32 - b));
+    }
+    const int e = -d, ws = e >> 5, b = e & 31;
+    const int i = w + ws;
+    uint32_t lo = (i >= 0 && i < nwords) ? row[i] : 0u;
+    if (b == 0) return lo;
+    uint32_t next = (i + 1 < nwords && i + 1 >= 0) ? row[i + 1] : 0u;
+    return (lo >> b) | (next << (32 - b));
+}
+
+__device__ __forceinline__ uint32_t compress_even_bits(uint32_t x)
+{
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// Emits the set bits of a [H][Ww] bitmap held in shared memory as list entries
+// base_id + y*W + x, row-major, into sites[] at a range reserved with one atomicAdd on *counter.
+__device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int W, int Ww, uint32_t base_id,
+                                           uint32_t *sites, int *counter, int *scratch)
+{
+    const int nwords = H * Ww;
+    const int per = (nwords + kThreads - 1) / kThreads;
+    const int w0 = threadIdx.x * per;
+    const int w1 = min(nwords, w0 + per);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(bm[w]);
+    int total;
+    int off = block_excl_scan(cnt, scratch, &total);
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = total > 0 ? atomicAdd(counter, total) : 0;
+    __syncthreads();
+    off += s_base;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = bm[w];
+        const int y = w / Ww, xb = (w - y * Ww) * 32;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            sites[off++] = base_id + (uint32_t)(y * W + xb + b);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: integration surface.  One CTA per stream.   integration.py:53-91
+//   t_L = max ts; delta = (t_L - t_prev) * leak; S = max(S - delta, 0);
+//   S[p] += 1 - (t_L - ts_j)*leak for the LAST event j on each distinct pixel p (numpy fancy `+=`);
+//   clamp again; frontier = {alive before, dead after} U {event pixels}.
+// Dynamic shared memory: hash_slots * 8 bytes (last-wins hash) + H*Ww*4 (frontier bitmap).
+// ---------------------------------------------------------------------------------------------
+struct IntegrateParams {
+    double *surface;        // [S][HW]
+    int *prev_ts;           // [S]
+    double *delta;          // [S]
+    uint8_t *active;        // [S]
+    uint32_t *front;        // [S][H*Ww]
+    const int32_t *events;  // [total][3] (y,x,ts)
+    const int32_t *offsets; // [S+1]
+    int *layer_counts;      // [n_layers] work-list counters, zeroed here for the step
+    int *err_flag;
+    int n_layers;
+    int H, W, Ww;
+    double leak;
+    int max_events, hash_slots;
+};
+
+__global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *hkey = reinterpret_cast<int *>(smem_raw);
+    int *hval = hkey + p.hash_slots;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(hval + p.hash_slots);
+    __shared__ int s_red[kThreads / 32];
+    __shared__ int s_tlast;
+
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int HW = p.H * p.W;
+    const int nbm = p.H * p.Ww;
+    if (s == 0 && tid < p.n_layers) p.layer_counts[tid] = 0;
+
+    const int e0 = p.offsets[s];
+    int n = p.offsets[s + 1] - e0;
+    uint32_t *front = p.front + (long long)s * nbm;
+    if (n > p.max_events) {
+        if (tid == 0) atomicOr(p.err_flag, 2);
+        n = 0;
+    }
+    if (n <= 0) {   // stream untouched by this step
+        if (tid == 0) { p.active[s] = 0; p.delta[s] = 0.0; }
+        for (int i = tid; i < nbm; i += kThreads) front[i] = 0u;
+        return;
+    }
+    const int32_t *ev = p.events + (long long)e0 * 3;
+
+    for (int i = tid; i < p.hash_slots; i += kThreads) { hkey[i] = -1; hval[i] = -1; }
+    for (int i = tid; i < nbm; i += kThreads) bm[i] = 0u;
+
+    // t_L = max(ts)
+    int tmax = INT_MIN;
+    for (int j = tid; j < n; j += kThreads) tmax = max(tmax, ev[3 * j + 2]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, d));
+    if ((tid & 31) == 0) s_red[tid >> 5] = tmax;
+    __syncthreads();
+    if (tid == 0) {
+        int m = s_red[0];
+        for (int i = 1; i < kThreads / 32; ++i) m = max(m, s_red[i]);
+        s_tlast = m;
+    }
+    __syncthreads();
+    const int t_last = s_tlast;
+    const int dt = (int)((unsigned)t_last - (unsigned)p.prev_ts[s]);   // int32 arithmetic like numpy
+    const double delta = __dmul_rn((double)dt, p.leak);
+
+    // last-duplicate-wins: hash pixel -> largest event index
+    const unsigned mask = (unsigned)p.hash_slots - 1u;
+    for (int j = tid; j < n; j += kThreads) {
+        const int y = ev[3 * j], x = ev[3 * j + 1];
+        if (y < 0 || y >= p.H || x < 0 || x >= p.W) { atomicOr(p.err_flag, 1); continue; }
+        const int pix = y * p.W + x;
+        unsigned h = ((unsigned)pix * 2654435761u) & mask;
+        while (true) {
+            const int k = atomicCAS(&hkey[h], -1, pix);
+            if (k == -1 || k == pix) { atomicMax(&hval[h], j); break; }
+            h = (h + 1) & mask;
+        }
+    }
+
+    // dense leak + clamp (integration.py:63-68)
+    double *surf = p.surface + (long long)s * HW;
+    for (int i = tid; i < HW; i += kThreads) {
+        const double v = surf[i];
+        const double w = __dsub_rn(v, delta);
+        const bool dead = w <= 0.0;
+        const double nv = dead ? 0.0 : w;
+        if (nv != v) surf[i] = nv;
+        if (v > 0.0 && dead) {
+            const int y = i / p.W, x = i - y * p.W;
+            atomicOr(&bm[y * p.Ww + (x >> 5)], 1u << (x & 31));
+        }
+    }
+    __syncthreads();
+
+    // event increments, last occurrence per pixel only (integration.py:71-74,80)
+    for (int j = tid; j < n; j += kThreads) {
+        const int y = ev[3 * j], x = ev[3 * j + 1];
+        if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+        const int pix = y * p.W + x;
+        unsigned h = ((unsigned)pix * 2654435761u) & mask;
+        while (hkey[h] != pix) h = (h + 1) & mask;
+        if (hval[h] != j) continue;
+        const int age = (int)((unsigned)t_last - (unsigned)ev[3 * j + 2]);
+        const double inc = __dsub_rn(1.0, __dmul_rn((double)age, p.leak));
+        double v = __dadd_rn(surf[pix], inc);
+        if (v <= 0.0) v = 0.0;
+        surf[pix] = v;
+        atomicOr(&bm[y * p.Ww + (x >> 5)], 1u << (x & 31));
+    }
+    __syncthreads();
+    for (int i = tid; i < nbm; i += kThreads) front[i] = bm[i];
+    if (tid == 0) { p.active[s] = 1; p.delta[s] = delta; p.prev_ts[s] = t_last; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: leak sweep of all conv layers.   conv2d.py:113-115,126-128
+//   F <- (float)((double)F - (double)A * delta)   [NEP-50 arithmetic of `f32 -= f32 * np.float64`]
+//   sites where sign(F >= 0) flipped in any channel are recorded in signchg.
+// Elements with A == 0 keep F bit-for-bit (x - 0 == x), so F is neither read nor written there.
+// Grid: (chunks per stream over all conv layers, S).
+// ---------------------------------------------------------------------------------------------
+struct SweepLayer {
+    float *F, *A;
+    uint32_t *signchg;
+    long long fstride;   // floats per stream (multiple of 4)
+    int n4;              // float4 per stream
+    int chunk0;          // first chunk index of this layer
+    int C, W, Ww, HWw;   // HWw = H*Ww
+};
+struct SweepParams {
+    SweepLayer L[kMaxConv];
+    int n_layers;
+    const double *delta;
+    const uint8_t *active;
+};
+constexpr int kSweepVec = 4;   // float4 per thread per chunk
+constexpr int kSweepChunk = kThreads * kSweepVec;
+
+__device__ __forceinline__ float leak1(float f, float a, double delta)
+{
+    return __double2float_rn(__dsub_rn((double)f, __dmul_rn((double)a, delta)));
+}
+
+__global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__ SweepParams p)
+{
+    const int s = blockIdx.y;
+    if (!p.active[s]) return;
+    const double delta = p.delta[s];
+    if (delta == 0.0) return;
+    int li = 0;
+    const int chunk = blockIdx.x;
+#pragma unroll 1
+    for (int i = 1; i < p.n_layers; ++i)
+        if (chunk >= p.L[i].chunk0) li = i;
+    const SweepLayer &L = p.L[li];
+    const int base = (chunk - L.chunk0) * kSweepChunk;
+    const float4 *A4 = reinterpret_cast<const float4 *>(L.A + (long long)s * L.fstride);
+    float4 *F4 = reinterpret_cast<float4 *>(L.F + (long long)s * L.fstride);
+
+    float4 a[kSweepVec];
+    int idx[kSweepVec];
+#pragma unroll
+    for (int j = 0; j < kSweepVec; ++j) {
+        idx[j] = base + j * kThreads + threadIdx.x;
+        a[j] = idx[j] < L.n4 ? A4[idx[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kSweepVec; ++j) {
+        const float4 av = a[j];
+        if (av.x == 0.f && av.y == 0.f && av.z == 0.f && av.w == 0.f) continue;
+        const float4 f = F4[idx[j]];
+        float4 g;
+        g.x = leak1(f.x, av.x, delta);
+        g.y = leak1(f.y, av.y, delta);
+        g.z = leak1(f.z, av.z, delta);
+        g.w = leak1(f.w, av.w, delta);
+        F4[idx[j]] = g;
+        const unsigned flips = ((f.x >= 0.f) != (g.x >= 0.f) ? 1u : 0u) | ((f.y >= 0.f) != (g.y >= 0.f) ? 2u : 0u) |
+                               ((f.z >= 0.f) != (g.z >= 0.f) ? 4u : 0u) | ((f.w >= 0.f) != (g.w >= 0.f) ? 8u : 0u);
+        if (flips) {
+            uint32_t *sc = L.signchg + (long long)s * L.HWw;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (flips & (1u << e)) {
+                    const int site = (idx[j] * 4 + e) / L.C;
+                    const int y = site / L.W, x = site - y * L.W;
+                    atomicOr(&sc[y * L.Ww + (x >> 5)], 1u << (x & 31));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: conv frontier.  One CTA per stream.   conv2d.py:118-131, cutils.pyx:73-112
+//   N = output sites whose receptive field holds an input event: o in [p+pad-k+1, p+pad] clipped
+//   (stride 1), i.e. a dilation of the previous layer's frontier bitmap;
+//   E = N U signchg  (output events);  N is appended to the cross-stream work list.
+// Dynamic shared memory: (Hin*WwIn + Hin*Ww + H*Ww) * 4 bytes.
+// ---------------------------------------------------------------------------------------------
+struct ConvFrontParams {
+    const uint32_t *prev_front;   // [S][Hin*WwIn]
+    uint32_t *front;              // [S][H*Ww]
+    uint32_t *signchg;            // [S][H*Ww]  (consumed: cleared)
+    const uint8_t *active;
+    uint32_t *sites;
+    int *counter;
+    int Hin, Win, WwIn;
+    int H, W, Ww;
+    int kh, kw, pad_t, pad_l;
+};
+
+__global__ void __launch_bounds__(kThreads) k_conv_frontier(ConvFrontParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *Hd = P + p.Hin * p.WwIn;
+    uint32_t *N = Hd + p.Hin * p.Ww;
+    __shared__ int scratch[9];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int nout = p.H * p.Ww;
+    uint32_t *front = p.front + (long long)s * nout;
+    if (!p.active[s]) {
+        for (int i = tid; i < nout; i += kThreads) front[i] = 0u;
+        return;
+    }
+    const uint32_t *pf = p.prev_front + (long long)s * p.Hin * p.WwIn;
+    for (int i = tid; i < p.Hin * p.WwIn; i += kThreads) P[i] = pf[i];
+    __syncthreads();
+    // horizontal: out x = in x + d, d in [pad_l-kw+1, pad_l]
+    const uint32_t lastmask = (p.W & 31) ? ((1u << (p.W & 31)) - 1u) : 0xffffffffu;
+    for (int i = tid; i < p.Hin * p.Ww; i += kThreads) {
+        const int y = i / p.Ww, w = i - y * p.Ww;
+        uint32_t acc = 0u;
+        for (int d = p.pad_l - p.kw + 1; d <= p.pad_l; ++d) acc |= row_shift(P + y * p.WwIn, p.WwIn, w, d);
+        if (w == p.Ww - 1) acc &= lastmask;
+        Hd[i] = acc;
+    }
+    __syncthreads();
+    // vertical: out y = in y + d, d in [pad_t-kh+1, pad_t]
+    uint32_t *sc = p.signchg + (long long)s * nout;
+    for (int i = tid; i < nout; i += kThreads) {
+        const int y = i / p.Ww, w = i - y * p.Ww;
+        uint32_t acc = 0u;
+        for (int d = p.pad_t - p.kh + 1; d <= p.pad_t; ++d) {
+            const int yi = y - d;
+            if (yi >= 0 && yi < p.Hin) acc |= Hd[yi * p.Ww + w];
+        }
+        N[i] = acc;
+        const uint32_t flips = sc[i];
+        if (flips) sc[i] = 0u;
+        front[i] = acc | flips;
+    }
+    __syncthreads();
+    emit_sites(N, p.H, p.W, p.Ww, (uint32_t)s * (uint32_t)(p.H * p.W), p.sites, p.counter, scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: pool frontier.  One CTA per stream.   maxpool.py:116-126,153-154
+//   hit = windows containing an input event; flags[hit] = False; W = hit U flags (sticky);
+//   output events = W (all evaluated windows); W is appended to the work list.
+// Dynamic shared memory: (Hin*WwIn + H*Ww) * 4 bytes.
+// ---------------------------------------------------------------------------------------------
+struct PoolFrontParams {
+    const uint32_t *prev_front;   // [S][Hin*WwIn]
+    uint32_t *front;              // [S][H*Ww]
+    uint32_t *flags;              // [S][H*Ww]
+    const uint8_t *active;
+    uint32_t *sites;
+    int *counter;
+    int Hin, Win, WwIn;
+    int H, W, Ww;
+    int kh, kw, stride;
+};
+
+__global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *Wb = P + p.Hin * p.WwIn;
+    __shared__ int scratch[9];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int nout = p.H * p.Ww;
+    uint32_t *front = p.front + (long long)s * nout;
+    if (!p.active[s]) {
+        for (int i = tid; i < nout; i += kThreads) front[i] = 0u;
+        return;
+    }
+    const uint32_t *pf = p.prev_front + (long long)s * p.Hin * p.WwIn;
+    for (int i = tid; i < p.Hin * p.WwIn; i += kThreads) P[i] = pf[i];
+    __syncthreads();
+    uint32_t *fl = p.flags + (long long)s * nout;
+    const uint32_t lastmask = (p.W & 31) ? ((1u << (p.W & 31)) - 1u) : 0xffffffffu;
+    for (int i = tid; i < nout; i += kThreads) {
+        const int oy = i / p.Ww, w = i - oy * p.Ww;
+        uint32_t hit = 0u;
+        if (p.kh == 2 && p.kw == 2 && p.stride == 2) {
+            const uint32_t *r0 = P + (2 * oy) * p.WwIn, *r1 = r0 + p.WwIn;
+            uint32_t lo = (2 * w < p.WwIn) ? (r0[2 * w] | r1[2 * w]) : 0u;
+            uint32_t hi = (2 * w + 1 < p.WwIn) ? (r0[2 * w + 1] | r1[2 * w + 1]) : 0u;
+            lo |= lo >> 1;
+            hi |= hi >> 1;
+            hit = compress_even_bits(lo) | (compress_even_bits(hi) << 16);
+        } else {
+            for (int b = 0; b < 32; ++b) {
+                const int ox = w * 32 + b;
+                if (ox >= p.W) break;
+                bool any = false;
+                for (int dy = 0; dy < p.kh && !any; ++dy)
+                    for (int dx = 0; dx < p.kw; ++dx) {
+                        const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+                        if ((P[iy * p.WwIn + (ix >> 5)] >> (ix & 31)) & 1u) { any = true; break; }
+                    }
+                if (any) hit |= 1u << b;
+            }
+        }
+        if (w == p.Ww - 1) hit &= lastmask;
+        const uint32_t f = fl[i] & ~hit;      // maxpool.py:118-120
+        const uint32_t wset = hit | f;        // maxpool.py:123-126
+        fl[i] = f;
+        Wb[i] = wset;
+        front[i] = wset;
+    }
+    __syncthreads();
+    emit_sites(Wb, p.H, p.W, p.Ww, (uint32_t)s * (uint32_t)(p.H * p.W), p.sites, p.counter, scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: pool evaluation over the work list.   maxpool.py:130-151, cutils.pyx:161-177
+//   per (window, channel): argmax of F over the window rows (ascending ky*kw+kx), ties -> smaller
+//   rate R = A*slope(F), then smaller row; argmin of R (first); unstable = R[argmax] != R[argmin];
+//   idx <- argmax; flags[window] |= any-channel unstable.
+// ---------------------------------------------------------------------------------------------
+struct PoolEvalParams {
+    const uint32_t *sites;
+    const int *counter;
+    unsigned long long *accum;    // work counter for the roofline
+    const float *F, *A;           // previous conv maps
+    long long fstride;
+    float alpha;
+    int cW;                       // previous conv width
+    uint8_t *idx;                 // [S][H*W*C]
+    long long istride;
+    uint32_t *flags;              // [S][H*Ww]
+    int C, H, W, Ww;
+    int kh, kw, stride;
+};
+
+__global__ void __launch_bounds__(kThreads) k_pool_eval(PoolEvalParams p)
+{
+    const int n = *p.counter;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.accum, (unsigned long long)n);
+    const long long total = (long long)n * p.C;
+    const int HW = p.H * p.W;
+    for (long long wi = (long long)blockIdx.x * kThreads + threadIdx.x; wi < total; wi += (long long)gridDim.x * kThreads) {
+        const uint32_t e = p.sites[wi / p.C];
+        const int c = (int)(wi % p.C);
+        const int s = (int)(e / (uint32_t)HW);
+        const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
+        const int oy = site / p.W, ox = site - oy * p.W;
+        const float *Fb = p.F + (long long)s * p.fstride;
+        const float *Ab = p.A + (long long)s * p.fstride;
+        int best = 0, low = 0;
+        float fbest = 0.f, rbest = 0.f, rlow = 0.f;
+        int row = 0;
+        for (int dy = 0; dy < p.kh; ++dy)
+            for (int dx = 0; dx < p.kw; ++dx, ++row) {
+                const long long off = ((long long)(oy * p.stride + dy) * p.cW + (ox * p.stride + dx)) * p.C + c;
+                const float f = Fb[off];
+                const float r = __fmul_rn(Ab[off], slope_of(f, p.alpha));
+                if (row == 0) {
+                    fbest = f; rbest = r; rlow = r;
+                } else {
+                    if (f > fbest) { best = row; fbest = f; rbest = r; }
+                    else if (f == fbest && r < rbest) { best = row; fbest = f; rbest = r; }
+                    if (r < rlow) { low = row; rlow = r; }
+                }
+            }
+        (void)low;
+        p.idx[(long long)s * p.istride + (long long)site * p.C + c] = (uint8_t)best;
+        const bool unstable = rbest != rlow;
+        // one atomic per (warp, window): lanes of the same window elect a leader
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, e);
+        const unsigned uns = __ballot_sync(act, unstable);
+        if (unstable && (__ffs(peers & uns) - 1) == (int)(threadIdx.x & 31))
+            atomicOr(&p.flags[(long long)s * p.H * p.Ww + oy * p.Ww + (ox >> 5)], 1u << (ox & 31));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: conv re-evaluation over the work list as a gathered GEMM.   conv2d.py:118-123,144-181
+//   for every listed site o:  F[o,:] = W^T . patch(V_prev, o) + b ;  A[o,:] = W^T . patch(R_prev, o)
+//   rows   = 2 per site (value row, rate row: same gather addresses, same weights)
+//   K      = kh*kw*Cin ordered (ky,kx,ci) - the HWIO weight layout flattened, channel-last gathers
+//   N      = Cout
+// Each output is accumulated sequentially over k in ONE thread, so the summation order does not
+// depend on where the site sits in a tile (identical patches -> identical bits, which keeps the
+// oracle's exact pool ties exact).
+// Tile: TS sites (2*TS rows) x BN outputs, K in chunks of BK; 256 threads, TM x TN per thread.
+// ---------------------------------------------------------------------------------------------
+struct ConvEvalParams {
+    const uint32_t *sites;
+    const int *counter;
+    unsigned long long *accum;
+    Src src;
+    const float *wgt;      // [Kpad][Npad], zero padded
+    const float *bias;     // [Npad]
+    float *F, *A;
+    long long fstride;
+    int C, H, W;           // output
+    int K, Kpad, Npad;
+    int kh, kw, pad_t, pad_l;
+};
+
+template <int BN, int TN, int TM, int BK>
+__global__ void __launch_bounds__(kThreads) k_conv_eval(ConvEvalParams p)
+{
+    constexpr int TX = BN / TN;            // threads along n
+    constexpr int TY = kThreads / TX;      // threads along rows
+    constexpr int ROWS = TY * TM;
+    constexpr int TS = ROWS / 2;           // sites per tile
+    constexpr int LDA = ROWS + 4;
+    constexpr int LDB = BN + 4;
+    static_assert(ROWS % 2 == 0 && TM <= TS && TS % TM == 0, "tile shape");
+    __shared__ __align__(16) float As[BK][LDA];
+    __shared__ __align__(16) float Bs[BK][LDB];
+    __shared__ int s_str[TS], s_y[TS], s_x[TS];
+
+    const int n_sites = *p.counter;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_sites > 0) atomicAdd(p.accum, (unsigned long long)n_sites);
+    const int m_tiles = (n_sites + TS - 1) / TS;
+    const int n_tiles = p.Npad / BN;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int HW = p.H * p.W;
+    const int Cin = p.src.C;
+    const bool vec = (Cin % 4 == 0) && (p.src.kind != 0);
+
+    for (int tile = blockIdx.x; tile < m_tiles * n_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int n0 = nt * BN;
+        __syncthreads();
+        for (int i = tid; i < TS; i += kThreads) {
+            const int gi = mt * TS + i;
+            if (gi < n_sites) {
+                const uint32_t e = p.sites[gi];
+                const int s = (int)(e / (uint32_t)HW);
+                const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
+                s_str[i] = s;
+                s_y[i] = site / p.W;
+                s_x[i] = site - (site / p.W) * p.W;
+            } else {
+                s_str[i] = -1;
+            }
+        }
+        float acc[TM][TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        __syncthreads();
+
+        for (int k0 = 0; k0 < p.Kpad; k0 += BK) {
+            // ---- gather the A-operand chunk: As[kk][site] = V, As[kk][TS+site] = R
+            if (vec) {
+                for (int u = tid; u < TS * (BK / 4); u += kThreads) {
+                    const int kg = u % (BK / 4), i = u / (BK / 4);
+                    const int k = k0 + 4 * kg;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), r = v;
+                    const int s = s_str[i];
+                    if (s >= 0 && k < p.K) {
+                        const int tap = k / Cin, c = k - tap * Cin;
+                        const int iy = s_y[i] + tap / p.kw - p.pad_t, ix = s_x[i] + tap % p.kw - p.pad_l;
+                        if (iy >= 0 && iy < p.src.H && ix >= 0 && ix < p.src.W) src_fetch4(p.src, s, iy, ix, c, v, r);
+                    }
+                    As[4 * kg + 0][i] = v.x; As[4 * kg + 1][i] = v.y; As[4 * kg + 2][i] = v.z; As[4 * kg + 3][i] = v.w;
+                    As[4 * kg + 0][TS + i] = r.x; As[4 * kg + 1][TS + i] = r.y;
+                    As[4 * kg + 2][TS + i] = r.z; As[4 * kg + 3][TS + i] = r.w;
+                }
+            } else {
+                for (int u = tid; u < TS * BK; u += kThreads) {
+                    const int kk = u % BK, i = u / BK;
+                    const int k = k0 + kk;
+                    float v = 0.f, r = 0.f;
+                    const int s = s_str[i];
+                    if (s >= 0 && k < p.K) {
+                        const int tap = k / Cin, c = k - tap * Cin;
+                        const int iy = s_y[i] + tap / p.kw - p.pad_t, ix = s_x[i] + tap % p.kw - p.pad_l;
+                        if (iy >= 0 && iy < p.src.H && ix >= 0 && ix < p.src.W) src_fetch(p.src, s, iy, ix, c, v, r);
+                    }
+                    As[kk][i] = v;
+                    As[kk][TS + i] = r;
+                }
+            }
+            // ---- weights chunk (padded on the host: always in bounds, 16-byte aligned)
+            for (int u = tid; u < BK * (BN / 4); u += kThreads) {
+                const int kk = u / (BN / 4), j = u % (BN / 4);
+                const float4 w = __ldg(reinterpret_cast<const float4 *>(p.wgt + (long long)(k0 + kk) * p.Npad + n0) + j);
+                *reinterpret_cast<float4 *>(&Bs[kk][4 * j]) = w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float a[TM], b[TN];
+#pragma unroll
+                for (int i = 0; i < TM; i += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(&As[kk][ty * TM + i]);
+                    a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+                }
+                if constexpr (TN % 4 == 0) {
+#pragma unroll
+                    for (int j = 0; j < TN; j += 4) {
+                        const float4 t = *reinterpret_cast<const float4 *>(&Bs[kk][tx * TN + j]);
+                        b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TN; j += 2) {
+                        const float2 t = *reinterpret_cast<const float2 *>(&Bs[kk][tx * TN + j]);
+                        b[j] = t.x; b[j + 1] = t.y;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+        // ---- epilogue: value rows get the bias and go to F, rate rows go to A
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int row = ty * TM + i;
+            const bool is_rate = row >= TS;
+            const int si = is_rate ? row - TS : row;
+            const int s = s_str[si];
+            if (s < 0) continue;
+            float *dst = (is_rate ? p.A : p.F) + (long long)s * p.fstride + ((long long)s_y[si] * p.W + s_x[si]) * p.C;
+            const int nb = n0 + tx * TN;
+            if (TN % 4 == 0 && (p.C & 3) == 0 && nb + TN <= p.C) {
+#pragma unroll
+                for (int j = 0; j < TN; j += 4) {
+                    float4 o = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+                    if (!is_rate) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + nb + j));
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                    }
+                    *reinterpret_cast<float4 *>(dst + nb + j) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const int n = nb + j;
+                    if (n < p.C) dst[n] = is_rate ? acc[i][j] : (acc[i][j] + p.bias[n]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: head = featuremap() of the last layer, channel-last (event_numpy.py:79,101).
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+    Src src;
+    float *out;          // [S][H*W*C]
+    int S;
+};
+
+__global__ void __launch_bounds__(kThreads) k_head(HeadParams p)
+{
+    const long long per = (long long)p.src.H * p.src.W * p.src.C;
+    const long long total = per * p.S;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int s = (int)(i / per);
+        const long long rem = i - (long long)s * per;
+        const int c = (int)(rem % p.src.C);
+        const int site = (int)(rem / p.src.C);
+        float v, r;
+        src_fetch(p.src, s, site / p.src.W, site % p.src.W, c, v, r);
+        p.out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: one stream's layer accessors, channel-last float32 (layer.py:53-81):
+//   surface (pre-activation, pool: gathered through argmax), layer_actfn (slope), conv_actfn (R),
+//   featuremap (V).  Any output pointer may be null.  Used by the Python Layer mirror only.
+// ---------------------------------------------------------------------------------------------
+struct ViewParams {
+    Src src;
+    int stream;
+    float *surface, *layer_actfn, *conv_actfn, *featuremap;
+};
+
+__global__ void __launch_bounds__(kThreads) k_layer_view(ViewParams p)
+{
+    const Src &q = p.src;
+    const long long per = (long long)q.H * q.W * q.C;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < per; i += (long long)gridDim.x * kThreads) {
+        const int c = (int)(i % q.C);
+        const int site = (int)(i / q.C);
+        const int y = site / q.W, x = site - y * q.W;
+        long long off;
+        if (q.kind == 1) {
+            off = i;
+        } else {
+            const int k = q.idx[(long long)p.stream * q.istride + i];
+            off = ((long long)(y * q.pstride + k / q.pkw) * q.cW + (x * q.pstride + k % q.pkw)) * q.C + c;
+        }
+        const float f = q.F[(long long)p.stream * q.fstride + off];
+        const float a = q.A[(long long)p.stream * q.fstride + off];
+        const float sl = slope_of(f, q.alpha);
+        if (p.surface) p.surface[i] = f;
+        if (p.layer_actfn) p.layer_actfn[i] = sl;
+        if (p.conv_actfn) p.conv_actfn[i] = __fmul_rn(a, sl);
+        if (p.featuremap) p.featuremap[i] = __fmul_rn(f, sl);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// utility kernels: reset / init plumbing
+// ---------------------------------------------------------------------------------------------
+// dst[s][i] = src[i] (or 0 when src == nullptr) for every stream with mask[s] != 0 (mask nullptr = all); 4-byte words.
+__global__ void __launch_bounds__(kThreads) k_broadcast_words(uint32_t *dst, const uint32_t *src, long long words,
+                                                               long long stride_words, const uint8_t *mask)
+{
+    const int s = blockIdx.y;
+    if (mask && !mask[s]) return;
+    uint32_t *d = dst + (long long)s * stride_words;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < words; i += (long long)gridDim.x * kThreads)
+        d[i] = src ? src[i] : 0u;
+}
+
+__global__ void __launch_bounds__(kThreads) k_reset_scalars(int *prev_ts, double *delta, uint8_t *active, const uint8_t *mask, int S)
+{
+    const int s = blockIdx.x * kThreads + threadIdx.x;
+    if (s >= S || (mask && !mask[s])) return;
+    prev_ts[s] = 0;
+    delta[s] = 0.0;
+    active[s] = 0;
+}
+
+// every site of stream 0 -> work list (used once, to evaluate the initial state)
+__global__ void __launch_bounds__(kThreads) k_all_sites(uint32_t *sites, int *counter, int HW)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < HW) sites[i] = (uint32_t)i;
+    if (i == 0) *counter = HW;
+}
+
+}  // namespace aec

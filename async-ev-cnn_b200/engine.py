@@ -1,0 +1,240 @@
+"""EventNetCuda - the multi-stream GPU engine behind the reference's event-mode model.
+
+One reference network object is one stream (src/models/event_numpy.py:53-105); this engine holds
+`n_streams` of them in one set of device arrays and advances all of them per call.  It is a thin
+Python veneer over the C ABI (include/aec.h): numpy in, numpy out, no arithmetic on the host.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+from .streams import parse_layers
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def pack_events(per_stream):
+    """list of int32 [B_s,3] arrays (None/empty = no events) -> (packed int32 [total,3], offsets int32 [S+1])."""
+    lens = [0 if e is None else len(e) for e in per_stream]
+    off = np.zeros(len(per_stream) + 1, np.int32)
+    np.cumsum(lens, out=off[1:])
+    if off[-1] == 0:
+        return np.zeros((0, 3), np.int32), off
+    ev = np.concatenate([np.asarray(e, np.int32).reshape(-1, 3) for e in per_stream if e is not None and len(e)])
+    return np.ascontiguousarray(ev), off
+
+
+class EventNetCuda:
+    """Integration -> (Conv | Pool)* chain for many streams on one GPU.
+
+    layers   'conv1=3,3,1,16 pool1=2,2 ...' or an OrderedDict name -> sizes (src/scripts/config.py:6-12)
+    weights  dict with 'w_<name>' [kh,kw,ci,co] and 'b_<name>' [co] (event_numpy.py:64)
+    """
+
+    def __init__(self, height, width, layers, weights, leak, alpha=0.1, padding="SAME", n_streams=1, device=0,
+                 max_events_per_step=0):
+        self._lib = N.lib()
+        self._h = ctypes.c_void_p()
+        self.height, self.width = int(height), int(width)
+        self.n_streams = int(n_streams)
+        self.leak, self.alpha = float(leak), float(alpha)
+        N.check(self._lib.aec_net_create(ctypes.byref(self._h), int(device), self.n_streams, self.height, self.width,
+                                         self.leak, int(max_events_per_step)))
+        self.names = ["intgr"]
+        if padding not in ("SAME", "VALID"):
+            raise ValueError("'padding' must be either 'SAME' or 'VALID', but %s has been provided." % padding)
+        pad = N.AEC_PAD_SAME if padding == "SAME" else N.AEC_PAD_VALID
+        for name, size in parse_layers(layers).items():
+            if "conv" in name:
+                w = np.ascontiguousarray(weights["w_" + name], dtype=np.float32)
+                b = np.ascontiguousarray(weights["b_" + name], dtype=np.float32)
+                kh, kw, ci, co = w.shape
+                N.check(self._lib.aec_net_add_conv(self._h, kh, kw, ci, co, _ptr(w), _ptr(b), 1, self.alpha, pad))
+            elif "pool" in name:
+                N.check(self._lib.aec_net_add_pool(self._h, int(size[0]), int(size[1]), int(size[0])))
+            else:
+                raise NotImplementedError("non-event layer %r (the EFCN configs have none)" % name)
+            self.names.append(name)
+        N.check(self._lib.aec_net_finalize(self._h))
+        self.infos = []
+        for i in range(len(self.names)):
+            info = N.LayerInfo()
+            N.check(self._lib.aec_net_layer_info(self._h, i, ctypes.byref(info)))
+            self.infos.append(info)
+        last = self.infos[-1]
+        self.head_shape = (last.height, last.width, last.channels)
+        self._head = np.empty((self.n_streams,) + self.head_shape, np.float32)
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self._lib.aec_net_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def shapes(self):
+        return [[i.channels, i.height, i.width] for i in self.infos]
+
+    def state_bytes_per_stream(self):
+        return int(self._lib.aec_net_state_bytes_per_stream(self._h))
+
+    def device_bytes(self):
+        return int(self._lib.aec_net_device_bytes(self._h))
+
+    def launch_count(self):
+        return int(self._lib.aec_net_launch_count(self._h))
+
+    # -- stepping -----------------------------------------------------------------------------
+    def reset(self, stream_mask=None, cuda_stream=None):
+        m = None if stream_mask is None else np.ascontiguousarray(stream_mask, dtype=np.uint8)
+        N.check(self._lib.aec_net_reset(self._h, _ptr(m), cuda_stream))
+
+    def _raise_events(self, err):
+        if err.code == N.AEC_EEVENTS:
+            raise IndexError(str(err)) from None
+        raise err
+
+    def step_packed(self, events, offsets, out=None, cuda_stream=None):
+        """Host->device->host step: events int32 [total,3], offsets int32 [S+1] -> head [S,H,W,C] float32."""
+        events = np.ascontiguousarray(events, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        assert offsets.shape == (self.n_streams + 1,)
+        out = self._head if out is None else out
+        try:
+            N.check(self._lib.aec_net_step_host(self._h, _ptr(events), _ptr(offsets), int(offsets[-1]), _ptr(out), cuda_stream))
+        except N.AecError as e:
+            self._raise_events(e)
+        return out
+
+    def step(self, per_stream_events, out=None):
+        """per_stream_events: list (length n_streams) of int32 [B_s,3] arrays, or one array when n_streams == 1."""
+        if isinstance(per_stream_events, np.ndarray) and per_stream_events.ndim == 2:
+            per_stream_events = [per_stream_events]
+        ev, off = pack_events(per_stream_events)
+        return self.step_packed(ev, off, out)
+
+    def step_device(self, events_ptr, offsets_ptr, total, cuda_stream=None):
+        """Asynchronous step on device-resident events (raw device pointers as ints)."""
+        N.check(self._lib.aec_net_step_device(self._h, ctypes.c_void_p(events_ptr), ctypes.c_void_p(offsets_ptr),
+                                              int(total), cuda_stream))
+
+    def head_device_ptr(self):
+        return int(self._lib.aec_net_head_device(self._h))
+
+    def begin_step(self, per_stream_events):
+        if isinstance(per_stream_events, np.ndarray) and per_stream_events.ndim == 2:
+            per_stream_events = [per_stream_events]
+        ev, off = pack_events(per_stream_events)
+        try:
+            N.check(self._lib.aec_net_begin_step(self._h, _ptr(ev), _ptr(off), int(off[-1]), None))
+        except N.AecError as e:
+            self._raise_events(e)
+
+    def layer_compute(self, layer):
+        N.check(self._lib.aec_net_layer_compute(self._h, int(layer), None))
+
+    def compute_head(self, stream=None):
+        N.check(self._lib.aec_net_compute_head(self._h, None))
+
+    # -- read-back (synchronising; parity tests and the Layer mirror) ------------------------------
+    def read(self, layer, what, stream=0):
+        size = N.check(self._lib.aec_net_read_size(self._h, layer, what))
+        info = self.infos[layer]
+        h, w, c, ww = info.height, info.width, info.channels, info.frontier_words_per_row
+        if what == N.AEC_READ_SURFACE:
+            buf = np.empty((h, w), np.float64)
+        elif what in (N.AEC_READ_F, N.AEC_READ_A, N.AEC_READ_INIT_F):
+            buf = np.empty((h, w, c), np.float32)
+        elif what in (N.AEC_READ_IDX, N.AEC_READ_INIT_IDX):
+            buf = np.empty((h, w, c), np.uint8)
+        else:
+            buf = np.empty((h, ww), np.uint32)
+        assert buf.nbytes == size
+        N.check(self._lib.aec_net_read(self._h, layer, what, stream, _ptr(buf), buf.nbytes))
+        return buf
+
+    def _bitmap_to_mask(self, bm, width):
+        bits = np.unpackbits(bm.view(np.uint8), axis=1, bitorder="little")
+        return bits[:, :width].astype(bool)
+
+    def frontier(self, layer, stream=0):
+        """bool [H,W] mask of the layer's output events of the last step."""
+        return self._bitmap_to_mask(self.read(layer, N.AEC_READ_FRONTIER, stream), self.infos[layer].width)
+
+    def state(self, layer, stream=0):
+        """State in the reference's layouts: {'S'} | {'F','A'} [C,H,W] | {'idx' [C,Ho,Wo], 'flags' [Ho,Wo]}."""
+        t = self.infos[layer].type
+        if t == N.AEC_LAYER_INTEGRATION:
+            return {"S": self.read(layer, N.AEC_READ_SURFACE, stream)}
+        if t == N.AEC_LAYER_CONV:
+            return {"F": np.ascontiguousarray(self.read(layer, N.AEC_READ_F, stream).transpose(2, 0, 1)),
+                    "A": np.ascontiguousarray(self.read(layer, N.AEC_READ_A, stream).transpose(2, 0, 1))}
+        return {"idx": np.ascontiguousarray(self.read(layer, N.AEC_READ_IDX, stream).transpose(2, 0, 1)),
+                "flags": self._bitmap_to_mask(self.read(layer, N.AEC_READ_FLAGS, stream), self.infos[layer].width)}
+
+    def init_state(self, layer):
+        t = self.infos[layer].type
+        if t == N.AEC_LAYER_CONV:
+            return {"F": np.ascontiguousarray(self.read(layer, N.AEC_READ_INIT_F, 0).transpose(2, 0, 1))}
+        if t == N.AEC_LAYER_POOL:
+            return {"idx": np.ascontiguousarray(self.read(layer, N.AEC_READ_INIT_IDX, 0).transpose(2, 0, 1))}
+        return {}
+
+    def view(self, layer, stream=0, which=("surface", "layer_actfn", "conv_actfn", "featuremap")):
+        """Layer accessors evaluated on the device, returned [C,H,W] float32 (layer.py:53-81)."""
+        info = self.infos[layer]
+        bufs = {k: np.empty((info.height, info.width, info.channels), np.float32) for k in which}
+        N.check(self._lib.aec_net_read_view(self._h, layer, stream, _ptr(bufs.get("surface")), _ptr(bufs.get("layer_actfn")),
+                                            _ptr(bufs.get("conv_actfn")), _ptr(bufs.get("featuremap"))))
+        return {k: np.ascontiguousarray(v.transpose(2, 0, 1)) for k, v in bufs.items()}
+
+    def step_info(self):
+        delta = np.empty(self.n_streams, np.float64)
+        active = np.empty(self.n_streams, np.uint8)
+        N.check(self._lib.aec_net_read_step_info(self._h, _ptr(delta), _ptr(active)))
+        return delta, active
+
+    def counters(self, reset=False):
+        """(sites re-evaluated per layer summed over streams and steps, steps issued) since the last reset."""
+        sites = np.zeros(len(self.names), np.uint64)
+        steps = ctypes.c_ulonglong(0)
+        N.check(self._lib.aec_net_read_counters(self._h, _ptr(sites), len(self.names), ctypes.byref(steps), 1 if reset else 0))
+        return sites, int(steps.value)
+
+
+class CudaAdapter:
+    """tests/parity.py adapter over one stream of an EventNetCuda (other streams get the same events
+    when `mirror` is set, to exercise the multi-stream path)."""
+
+    def __init__(self, net, stream=0, mirror=True):
+        self.net, self.stream, self.mirror = net, stream, mirror
+        self.names = net.names
+
+    def step(self, events):
+        if self.mirror:
+            per = [events] * self.net.n_streams
+        else:
+            per = [None] * self.net.n_streams
+            per[self.stream] = events
+        return self.net.step(per)[self.stream].copy()
+
+    def delta(self):
+        return self.net.step_info()[0][self.stream]
+
+    def frontier(self, i):
+        return self.net.frontier(i, self.stream)
+
+    def state(self, i):
+        return self.net.state(i, self.stream)

@@ -1,0 +1,65 @@
+"""GPU: BASELINE-size checks through size-independent properties (the oracle is too slow for
+thousands of streams): replicated streams agree bit-for-bit, runs are deterministic, a stream's
+result does not depend on which other streams share the batch, and the event net equals a dense
+torch fp32 frame network."""
+import numpy as np
+import pytest
+
+import async_ev_cnn_b200 as P
+from async_ev_cnn_b200.engine import EventNetCuda
+
+pytestmark = pytest.mark.gpu
+H, W = 160, 224
+
+
+def _run(net, evs, steps):
+    heads = []
+    for t in range(steps):
+        heads.append(net.step([evs[s % evs.shape[0], t] for s in range(net.n_streams)]).copy())
+    return np.stack(heads)
+
+
+def test_replicas_determinism_and_batch_independence():
+    wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
+    evs = P.synthetic_events("edge", 4, 12, 200, H, W, seed=3)
+    net = EventNetCuda(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=64)
+    a = _run(net, evs, 12)
+    for s in range(4, 64):                              # stream s replays stream s % 4
+        assert np.array_equal(a[:, s], a[:, s % 4])
+    net.reset()
+    b = _run(net, evs, 12)
+    assert np.array_equal(a, b)                         # deterministic, reset restores the initial state
+    net.close()
+    small = EventNetCuda(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=4)
+    c = _run(small, evs, 12)
+    assert np.array_equal(c, a[:, :4])                  # result independent of batch composition
+    sites, steps = small.counters()
+    assert steps == 12 and sites[1] > 0
+    small.close()
+
+
+def test_efcn_event_equals_dense_torch_frame_network():
+    """configs/efcn_frame_np.yml shape: dense conv -> leaky -> max_pool on the integrated frame."""
+    import torch
+    import torch.nn.functional as F
+    from oracle.event_oracle import integrate_frame
+    wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
+    evs = P.synthetic_events("uniform", 1, 16, 200, H, W, seed=5)[0]
+    net = EventNetCuda(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=1)
+    state = None
+    for t in range(16):
+        head = net.step(evs[t])[0]
+        frame, ts = integrate_frame(evs[t], 5e-5, H, W, state)
+        state = (frame, ts)
+    x = torch.from_numpy(frame)[None, None].double().cuda()
+    for name, size in P.parse_layers(P.EFCN_LAYERS).items():
+        if "conv" in name:
+            k = torch.from_numpy(wts["w_" + name]).permute(3, 2, 0, 1).double().cuda()
+            x = F.conv2d(x, k, torch.from_numpy(wts["b_" + name]).double().cuda(), padding=(size[0] - 1) // 2)
+            x = torch.maximum(x, 0.1 * x)
+        else:
+            x = F.max_pool2d(x, size[0], size[0])
+    dense = x[0].permute(1, 2, 0).cpu().numpy()
+    scale = np.abs(dense).max()
+    assert np.abs(head - dense).max() <= 1e-4 * scale, "event vs dense frame: %.3e (scale %.3e)" % (np.abs(head - dense).max(), scale)
+    net.close()

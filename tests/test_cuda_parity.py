@@ -1,0 +1,174 @@
+"""GPU: the CUDA path (through the C ABI) against the golden vectors minted from the reference and
+against the live CPU oracle.  Bars: frontier sets / argmax / flags bit-exact; float maps within
+1e-4 relative (parity.FLOAT_RTOL); nets with exactly-representable arithmetic bit-equal."""
+import numpy as np
+import pytest
+
+import async_ev_cnn_b200 as P
+from async_ev_cnn_b200.engine import CudaAdapter, EventNetCuda
+from oracle.event_oracle import OracleEventNet, dense_forward, integrate_frame
+from parity import (FLOAT_RTOL, Golden, OracleAdapter, assert_close_map, compare_live, golden_path, replay_golden)
+
+pytestmark = pytest.mark.gpu
+
+SMALL = "conv1=3,3,1,4 pool1=2,2 conv2=3,3,4,8 pool2=2,2 conv3=1,1,8,6"
+DEEP = "conv1=3,3,1,8 conv1b=3,3,8,8 pool1=2,2 conv2=3,3,8,16 conv2b=1,1,16,12 pool2=2,2 conv3=3,3,12,20"
+
+
+@pytest.mark.parametrize("case,exact,n_streams", [
+    ("small32_exact", True, 3),
+    ("ragged16", True, 2),
+    ("proto8x8", False, 1),
+    ("small32_float", False, 2),
+    ("efcn_edge", False, 2),
+    ("efcn_uniform", False, 1),
+])
+def test_cuda_matches_reference_golden(case, exact, n_streams):
+    g = Golden(golden_path(case))
+    net = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=n_streams)
+    assert net.shapes() == g.shapes()
+    for i, nm in enumerate(g.names):           # state after construction
+        st = net.init_state(i)
+        if "F" in st:
+            assert_close_map(st["F"], g.z["init_F_%s" % nm], exact, "init F %s" % nm)
+        if "idx" in st:
+            assert np.array_equal(st["idx"], g.z["init_idx_%s" % nm])
+    replay_golden(CudaAdapter(net, stream=n_streams - 1), g, exact=exact, steps=150)
+    net.close()
+
+
+@pytest.mark.parametrize("kind,layers,h,w,batch", [
+    ("uniform", SMALL, 32, 48, 24),
+    ("edge", DEEP, 40, 64, 30),
+])
+def test_many_streams_against_live_oracle_exact(kind, layers, h, w, batch):
+    """Different events per stream; arithmetic exactly representable -> everything bit-equal."""
+    S, steps = 6, 60
+    wts = P.xavier_weights(layers, seed=9, exact=True)
+    evs = P.synthetic_events(kind, S, steps, batch, h, w, seed=5, dt_int=(1, 5))
+    net = EventNetCuda(h, w, layers, wts, 1.0 / 64, 0.5, "SAME", n_streams=S)
+    oracles = [OracleEventNet(h, w, layers, wts, 1.0 / 64, 0.5, "SAME") for _ in range(S)]
+    for t in range(steps):
+        per = [evs[s, t] if (s + t) % 5 else None for s in range(S)]     # some streams idle in some steps
+        heads = net.step(per)
+        delta, active = net.step_info()
+        for s in range(S):
+            if per[s] is None:
+                assert not active[s]
+                continue
+            ho = oracles[s].step(per[s])
+            assert active[s] and delta[s] == oracles[s].delta
+            assert np.array_equal(heads[s], ho), "step %d stream %d head" % (t, s)
+        if t % 10 == 9:
+            for s in range(S):
+                oa = OracleAdapter(oracles[s])
+                for i in range(len(net.names)):
+                    so, sc = oa.state(i), net.state(i, s)
+                    for key in so:
+                        assert np.array_equal(sc[key], so[key]), "step %d stream %d layer %s %s" % (t, s, net.names[i], key)
+                    if per[s] is not None:
+                        assert np.array_equal(net.frontier(i, s), oa.frontier(i))
+    net.close()
+
+
+def test_float_net_against_live_oracle_with_explained_mismatches():
+    h, w, steps = 48, 64, 120
+    wts = P.xavier_weights(DEEP, seed=2)
+    evs = P.synthetic_events("uniform", 1, steps, 40, h, w, seed=8, dt_int=(1, 12))[0]
+    net = EventNetCuda(h, w, DEEP, wts, 0.004, 0.1, "SAME", n_streams=1)
+    ora = OracleEventNet(h, w, DEEP, wts, 0.004, 0.1, "SAME")
+    tolerated = compare_live(CudaAdapter(net), OracleAdapter(ora), list(evs), exact=False)
+    total = sum(int(np.prod(s[1:])) for s in net.shapes()) * steps
+    assert tolerated <= 1e-4 * total, "too many near-zero frontier disagreements: %d" % tolerated
+    net.close()
+
+
+def test_layer_at_a_time_equals_fused_step():
+    g = Golden(golden_path("small32_float"))
+    a = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=2)
+    b = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=2)
+    for s in range(40):
+        ev = g.events(s)
+        ha = a.step([ev, ev])
+        b.begin_step([ev, ev])
+        for li in range(1, len(b.names)):
+            b.layer_compute(li)
+        b.compute_head()
+        for li in range(len(a.names)):
+            sa, sb = a.state(li, 1), b.state(li, 1)
+            for k in sa:
+                assert np.array_equal(sa[k], sb[k])
+            assert np.array_equal(a.frontier(li, 1), b.frontier(li, 1))
+    a.close()
+    b.close()
+
+
+def test_reset_mask_and_idle_streams():
+    g = Golden(golden_path("small32_exact"))
+    net = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=3)
+    for s in range(10):
+        net.step([g.events(s), g.events(s), None])
+    fresh = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=1)
+    for li in range(len(net.names)):          # stream 2 never received events: still the initial state
+        a, b = net.state(li, 2), fresh.state(li, 0)
+        for k in a:
+            assert np.array_equal(a[k], b[k])
+    net.reset(stream_mask=[0, 1, 0])
+    for li in range(len(net.names)):
+        a, b = net.state(li, 1), fresh.state(li, 0)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), "reset stream differs at %s" % net.names[li]
+    # stream 0 kept its state; replaying the fixture from step 10 on it must still match the golden
+    ad = CudaAdapter(net, stream=0, mirror=False)
+    for s in range(10, 30):
+        head = ad.step(g.events(s))
+        assert np.array_equal(head, g.z["heads"][s])
+    # the reset stream restarted from scratch
+    ad1 = CudaAdapter(net, stream=1, mirror=False)
+    for s in range(0, 10):
+        assert np.array_equal(ad1.step(g.events(s)), g.z["heads"][s])
+    net.close()
+    fresh.close()
+
+
+def test_bad_events_raise_like_the_reference():
+    g = Golden(golden_path("small32_exact"))
+    net = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=1, max_events_per_step=16)
+    with pytest.raises(IndexError):
+        net.step(np.array([[g.height, 0, 5]], np.int32))          # y out of range (reference: IndexError)
+    with pytest.raises(IndexError):
+        net.step(np.zeros((17, 3), np.int32))                      # more than max_events_per_step
+    with pytest.raises(ValueError):
+        EventNetCuda(8, 8, "conv1=3,3,1,1", {"w_conv1": np.zeros((3, 3, 1, 1)), "b_conv1": np.zeros(1)}, 0.1, padding="FULL")
+    with pytest.raises(Exception):
+        EventNetCuda(9, 9, "conv1=3,3,1,1 pool1=2,2", {"w_conv1": np.zeros((3, 3, 1, 1)), "b_conv1": np.zeros(1)}, 0.1)
+    net.close()
+
+
+def test_valid_padding_and_odd_kernels_exact():
+    layers = "conv1=5,5,1,4 conv2=3,3,4,4 pool1=2,2 conv3=1,1,4,4"
+    h, w = 30, 34                                      # VALID: 30x34 -> 26x30 -> 24x28 -> 12x14
+    wts = P.xavier_weights(layers, seed=6, exact=True)
+    evs = P.synthetic_events("uniform", 1, 50, 15, h, w, seed=4, dt_int=(1, 5))[0]
+    net = EventNetCuda(h, w, layers, wts, 1.0 / 64, 0.5, "VALID", n_streams=1)
+    ora = OracleEventNet(h, w, layers, wts, 1.0 / 64, 0.5, "VALID")
+    assert compare_live(CudaAdapter(net), OracleAdapter(ora), list(evs), exact=True) == 0
+    net.close()
+
+
+def test_event_vs_frame_equivalence_on_gpu():
+    """test_correctness.py protocol with the CUDA event net: event-driven == dense frame network."""
+    g = Golden(golden_path("proto8x8"))
+    w = g.weights()
+    net = EventNetCuda(g.height, g.width, g.layers, w, g.leak, g.alpha, "SAME", n_streams=1)
+    state = None
+    for s in range(300):
+        ev = g.events(s)
+        frame, ts = integrate_frame(ev, g.leak, g.height, g.width, state)
+        state = (frame, ts)
+        net.step(ev)
+        dense = dense_forward(frame, g.layers, w, g.alpha, "SAME")
+        for i, d in enumerate(dense, start=1):
+            fm = net.view(i, 0, which=("featuremap",))["featuremap"]
+            assert np.allclose(fm, d, rtol=1e-5, atol=1e-5), "step %d layer %s" % (s, net.names[i])
+    net.close()
