@@ -19,7 +19,8 @@ SYMBOLS = [
     "aec_net_state_bytes_per_stream", "aec_net_device_bytes", "aec_net_reset", "aec_net_step_device",
     "aec_net_step_host", "aec_net_head_device", "aec_net_head_elems_per_stream", "aec_net_begin_step",
     "aec_net_layer_compute", "aec_net_compute_head", "aec_net_read_size", "aec_net_read", "aec_net_read_step_info",
-    "aec_net_read_counters", "aec_net_launch_count", "aec_net_read_view",
+    "aec_net_read_counters", "aec_net_launch_count", "aec_net_read_view", "aec_net_profile", "aec_net_read_profile",
+    "aec_net_count_nonzero_rate_groups",
 ]
 
 
@@ -97,6 +98,12 @@ def lib():
     L.aec_net_read_counters.argtypes = [vp, vp, i, ctypes.POINTER(ull), i]
     L.aec_net_read_view.restype = i
     L.aec_net_read_view.argtypes = [vp, i, i, vp, vp, vp, vp]
+    L.aec_net_profile.restype = i
+    L.aec_net_profile.argtypes = [vp, i]
+    L.aec_net_read_profile.restype = i
+    L.aec_net_read_profile.argtypes = [vp, vp, i, ctypes.POINTER(ull)]
+    L.aec_net_count_nonzero_rate_groups.restype = i
+    L.aec_net_count_nonzero_rate_groups.argtypes = [vp, ctypes.POINTER(ull), ctypes.POINTER(ull)]
     L.aec_net_launch_count.restype = ull
     L.aec_net_launch_count.argtypes = [vp]
     _lib = L

@@ -76,6 +76,12 @@ struct aec_net {
     SweepParams sweep_all;
     unsigned long long launches = 0, steps = 0;
     int conv_eval_blocks[4] = {0, 0, 0, 0};
+    // per-launch timing (aec_net_profile): one CUDA event between consecutive launches of a step
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // events of the current step (n_slots + 1)
+    std::vector<double> prof_ms;            // accumulated ms per slot
+    int prof_slot = 0;
+    unsigned long long prof_steps = 0;
     float *view = nullptr;      // 4 x max(H*W*C) scratch for aec_net_read_view
     size_t view_elems = 0;
 };
@@ -241,6 +247,35 @@ static int launch_check(aec_net *n, const char *what)
     return AEC_OK;
 }
 
+// Profiling: an event is recorded on the launching stream after every launch of a step, so the
+// elapsed time between consecutive events is that kernel's duration inside the real step.
+static int prof_mark(aec_net *n, cudaStream_t st)
+{
+    if (!n->profiling) return AEC_OK;
+    if (n->prof_slot >= (int)n->prof_events.size()) {
+        cudaEvent_t ev;
+        CU(cudaEventCreate(&ev));
+        n->prof_events.push_back(ev);
+    }
+    CU(cudaEventRecord(n->prof_events[n->prof_slot++], st));
+    return AEC_OK;
+}
+
+static int prof_collect(aec_net *n, cudaStream_t st)
+{
+    if (!n->profiling || n->prof_slot < 2) return AEC_OK;
+    CU(cudaStreamSynchronize(st));
+    if ((int)n->prof_ms.size() < n->prof_slot - 1) n->prof_ms.resize(n->prof_slot - 1, 0.0);
+    for (int i = 0; i + 1 < n->prof_slot; ++i) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, n->prof_events[i], n->prof_events[i + 1]));
+        n->prof_ms[i] += ms;
+    }
+    n->prof_steps++;
+    n->prof_slot = 0;
+    return AEC_OK;
+}
+
 static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cudaStream_t st)
 {
     const HostLayer &l = n->L[0];
@@ -250,8 +285,11 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
     p.n_layers = (int)n->L.size();
     p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.leak = n->leak; p.max_events = n->max_events; p.hash_slots = n->hash_slots;
     const size_t smem = (size_t)n->hash_slots * 8 + (size_t)l.H * l.Ww * 4;
+    int rc;
+    if ((rc = prof_mark(n, st))) return rc;
     k_integrate<<<n->S, kThreads, smem, st>>>(p);
-    return launch_check(n, "k_integrate");
+    if ((rc = launch_check(n, "k_integrate"))) return rc;
+    return prof_mark(n, st);
 }
 
 static void fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0)
@@ -267,7 +305,8 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
         if (n->sweep_all.n_layers == 0) return AEC_OK;
         dim3 grid(n->sweep_chunks, n->S);
         k_leak_sweep<<<grid, kThreads, 0, st>>>(n->sweep_all);
-        return launch_check(n, "k_leak_sweep");
+        int rc = launch_check(n, "k_leak_sweep");
+        return rc ? rc : prof_mark(n, st);
     }
     SweepParams p;
     memset(&p, 0, sizeof p);
@@ -293,7 +332,8 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
     case 64: k_conv_eval<64, 4, 8, 16><<<n->conv_eval_blocks[2], kThreads, 0, st>>>(p); break;
     default: k_conv_eval<128, 8, 8, 16><<<n->conv_eval_blocks[3], kThreads, 0, st>>>(p); break;
     }
-    return launch_check(n, "k_conv_eval");
+    int rc = launch_check(n, "k_conv_eval");
+    return rc ? rc : prof_mark(n, st);
 }
 
 static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
@@ -306,7 +346,8 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     p.idx = l.idx; p.istride = l.fstride; p.flags = l.flags;
     p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
     k_pool_eval<<<n->num_sms * 8, kThreads, 0, st>>>(p);
-    return launch_check(n, "k_pool_eval");
+    int rc = launch_check(n, "k_pool_eval");
+    return rc ? rc : prof_mark(n, st);
 }
 
 static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
@@ -324,6 +365,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
         const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4;
         k_conv_frontier<<<n->S, kThreads, smem, st>>>(p);
         if ((rc = launch_check(n, "k_conv_frontier"))) return rc;
+        if ((rc = prof_mark(n, st))) return rc;
         return run_conv_eval(n, li, st);
     }
     PoolFrontParams p;
@@ -334,6 +376,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4;
     k_pool_frontier<<<n->S, kThreads, smem, st>>>(p);
     if ((rc = launch_check(n, "k_pool_frontier"))) return rc;
+    if ((rc = prof_mark(n, st))) return rc;
     return run_pool_eval(n, li, st);
 }
 
@@ -346,7 +389,8 @@ static int run_head(aec_net *n, cudaStream_t st)
     long long total = (long long)n->head_per_stream * n->S;
     int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
     k_head<<<blocks, kThreads, 0, st>>>(p);
-    return launch_check(n, "k_head");
+    int rc = launch_check(n, "k_head");
+    return rc ? rc : prof_mark(n, st);
 }
 
 static int broadcast(aec_net *n, void *dst, const void *src, long long bytes_per_stream, long long stride_bytes,
@@ -549,7 +593,7 @@ extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t 
         if ((rc = run_layer(n, li, false, st))) return rc;
     if ((rc = run_head(n, st))) return rc;
     n->steps++;
-    return AEC_OK;
+    return prof_collect(n, st);
 }
 
 static int upload_events(aec_net *n, const int32_t *ev, const int32_t *off, int total, cudaStream_t st)
@@ -711,5 +755,42 @@ extern "C" int aec_net_read_view(aec_net *n, int layer, int stream, float *surfa
     if (layer_actfn) CU(cudaMemcpy(layer_actfn, p.layer_actfn, per * 4, cudaMemcpyDeviceToHost));
     if (conv_actfn) CU(cudaMemcpy(conv_actfn, p.conv_actfn, per * 4, cudaMemcpyDeviceToHost));
     if (featuremap) CU(cudaMemcpy(featuremap, p.featuremap, per * 4, cudaMemcpyDeviceToHost));
+    return AEC_OK;
+}
+
+extern "C" int aec_net_profile(aec_net *n, int enable)
+{
+    NEED_FINAL(n);
+    n->profiling = enable != 0;
+    n->prof_slot = 0;
+    n->prof_steps = 0;
+    std::fill(n->prof_ms.begin(), n->prof_ms.end(), 0.0);
+    return AEC_OK;
+}
+
+extern "C" int aec_net_read_profile(aec_net *n, double *ms_per_slot, int n_slots, unsigned long long *steps)
+{
+    NEED_FINAL(n);
+    for (int i = 0; i < n_slots; ++i) ms_per_slot[i] = i < (int)n->prof_ms.size() ? n->prof_ms[i] : 0.0;
+    if (steps) *steps = n->prof_steps;
+    return (int)n->prof_ms.size();
+}
+
+extern "C" int aec_net_count_nonzero_rate_groups(aec_net *n, unsigned long long *nz_groups, unsigned long long *total_groups)
+{
+    NEED_FINAL(n);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
+    unsigned long long total = 0;
+    for (int i = 0; i < n->sweep_all.n_layers; ++i) total += (unsigned long long)n->sweep_all.L[i].n4 * n->S;
+    if (n->sweep_all.n_layers) {
+        dim3 grid(n->sweep_chunks, n->S);
+        k_count_nz4<<<grid, kThreads>>>(n->sweep_all, n->accum + 31);
+        int rc = launch_check(n, "k_count_nz4");
+        if (rc) return rc;
+    }
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(nz_groups, n->accum + 31, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (total_groups) *total_groups = total;
     return AEC_OK;
 }

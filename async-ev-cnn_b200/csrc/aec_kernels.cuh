@@ -810,6 +810,34 @@ __global__ void __launch_bounds__(kThreads) k_layer_view(ViewParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// K9: measurement helper - number of float4 groups of the leak-rate maps A holding a non-zero
+// (the groups for which the leak sweep must read and write F).  Not on the hot path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_count_nz4(const __grid_constant__ SweepParams p, unsigned long long *out)
+{
+    const int s = blockIdx.y;
+    int li = 0;
+    const int chunk = blockIdx.x;
+#pragma unroll 1
+    for (int i = 1; i < p.n_layers; ++i)
+        if (chunk >= p.L[i].chunk0) li = i;
+    const SweepLayer &L = p.L[li];
+    const int base = (chunk - L.chunk0) * kSweepChunk;
+    const float4 *A4 = reinterpret_cast<const float4 *>(L.A + (long long)s * L.fstride);
+    int cnt = 0;
+    for (int j = 0; j < kSweepVec; ++j) {
+        const int idx = base + j * kThreads + threadIdx.x;
+        if (idx < L.n4) {
+            const float4 a = A4[idx];
+            cnt += (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
 // utility kernels: reset / init plumbing
 // ---------------------------------------------------------------------------------------------
 // dst[s][i] = src[i] (or 0 when src == nullptr) for every stream with mask[s] != 0 (mask nullptr = all); 4-byte words.

@@ -214,6 +214,33 @@ class EventNetCuda:
         return sites, int(steps.value)
 
 
+    # -- measurement ---------------------------------------------------------------------------
+    def slot_names(self):
+        """Names of the launches of one step, in order (matches aec_net_read_profile slots)."""
+        names = ["surface", "leak_sweep"]
+        for nm in self.names[1:]:
+            names += [nm + ".frontier", nm + ".eval"]
+        return names + ["head"]
+
+    def profile(self, enable=True):
+        N.check(self._lib.aec_net_profile(self._h, 1 if enable else 0))
+
+    def read_profile(self):
+        """-> (dict slot name -> mean ms per step, steps profiled)."""
+        names = self.slot_names()
+        # slot i = time between mark i and mark i+1; mark 0 precedes the surface kernel
+        ms = np.zeros(len(names) + 4, np.float64)
+        steps = ctypes.c_ulonglong(0)
+        n = N.check(self._lib.aec_net_read_profile(self._h, _ptr(ms), len(ms), ctypes.byref(steps)))
+        k = max(1, int(steps.value))
+        return {names[i]: ms[i] / k for i in range(min(n, len(names)))}, int(steps.value)
+
+    def nonzero_rate_fraction(self):
+        nz, tot = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        N.check(self._lib.aec_net_count_nonzero_rate_groups(self._h, ctypes.byref(nz), ctypes.byref(tot)))
+        return nz.value / max(1, tot.value), int(tot.value)
+
+
 class CudaAdapter:
     """tests/parity.py adapter over one stream of an EventNetCuda (other streams get the same events
     when `mirror` is set, to exercise the multi-stream path)."""

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py - EFCN event-mode throughput (events/s) on B200, next to the host-core CPU baseline.
+
+    python bench.py --gpus 1 --steps K --warmup W                 (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): EFCN of configs/efcn_event.yml
+(5 x [3x3 conv + 2x2 pool] + two 1x1 convs -> 5x7x110) on 160x224 frames (the 240x180-sensor stream
+centre-cropped as the config does), leak 5e-5/us, alpha 0.1, B = 200 events per stream per step,
+random-init weights (xavier, seed 0), seeded synthetic streams.  A "step" advances EVERY stream by
+one batch of B events; streams are independent, `--streams` of them per GPU (weak scaling: per-GPU
+work fixed, no data-path collective).  Before timing, every stream is pre-rolled to the steady
+state of the leaky surface (1/leak = 20 ms = 40 steps) so the frontier sizes are the real ones.
+
+One JSON line is printed by rank 0 (see the keys at the bottom).  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, LEAK, ALPHA = 160, 224, 5e-5, 0.1
+METRIC = "efcn_event_inference_throughput"
+UNIT = "events/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="concurrent event streams PER GPU")
+    ap.add_argument("--batch", type=int, default=200, help="events per stream per step (batch_event_size)")
+    ap.add_argument("--kind", default="edge", choices=["edge", "uniform"], help="synthetic stream kind (SURVEY 8d)")
+    ap.add_argument("--preroll", type=int, default=48, help="untimed steps to reach the surface's steady state")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="timed CPU work per core for the baseline")
+    ap.add_argument("--cpu-worker", type=int, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-steps", type=int, default=0, help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle port (one reference-style network object per stream, one process per core)
+# ------------------------------------------------------------------------------------------------
+def cpu_worker(args):
+    """One process = one stream on one core, OMP_NUM_THREADS=1.  Times only the
+    compute chain + final featuremap, as runner.py:84-89 does for the event runner."""
+    import async_ev_cnn_b200 as P
+    from oracle.event_oracle import OracleEventNet
+    seed = args.cpu_worker
+    wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
+    net = OracleEventNet(H, W, P.EFCN_LAYERS, wts, LEAK, ALPHA, "SAME")
+    max_steps = args.cpu_steps if args.cpu_steps > 0 else 2000
+    n_steps = args.preroll + args.warmup + max_steps
+    evs = P.synthetic_events(args.kind, 1, n_steps, args.batch, H, W, seed=1000 + seed)[0]
+    t = 0
+    for _ in range(args.preroll + args.warmup):
+        net.step(evs[t])
+        t += 1
+    done = 0
+    t0 = time.perf_counter()
+    while done < max_steps:
+        net.step(evs[t])
+        t += 1
+        done += 1
+        if args.cpu_steps <= 0 and time.perf_counter() - t0 >= args.cpu_seconds:
+            break
+    dt = time.perf_counter() - t0
+    print(json.dumps({"steps": done, "seconds": dt}))
+
+
+def run_cpu_processes(args, fixed_steps):
+    """Runs one worker per host core concurrently; returns (aggregate events/s, cores, per-core steps, seconds)."""
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--kind", args.kind, "--batch", str(args.batch),
+           "--preroll", str(args.preroll), "--warmup", str(max(args.warmup, 2)), "--cpu-seconds", str(args.cpu_seconds),
+           "--cpu-steps", str(fixed_steps)]
+    procs = [subprocess.Popen(cmd + ["--cpu-worker", str(i)], stdout=subprocess.PIPE, env=env, text=True) for i in range(cores)]
+    rate, steps, secs = 0.0, [], []
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("CPU baseline worker failed")
+        r = json.loads(out.strip().splitlines()[-1])
+        rate += r["steps"] * args.batch / r["seconds"]
+        steps.append(r["steps"])
+        secs.append(r["seconds"])
+    return rate, cores, steps, secs
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores.
+    The reference is Python + one Cython module and cannot travel to the GPU box, so this times the
+    oracle port (bit-identical to the reference and equally fast: tests/test_oracle_vs_reference.py),
+    one stream per core on all cores; a step = every core advances its stream by one batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    rate, cores, st, secs = run_cpu_processes(args, fixed_steps=steps)
+    ms = 1e3 * float(np.mean(secs)) / steps
+    sample = "%d cores x 1 stream x %d steps x %d events (%s stream, %d pre-roll steps)" % (cores, steps, args.batch, args.kind, args.preroll)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.streams),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, streams):
+    return {"workload": "configs/efcn_event.yml EFCN event-mode, 160x224 (240x180 sensor centre-cropped), B=%d events/stream/step, "
+                        "synthetic %s streams, random-init weights" % (args.batch, args.kind),
+            "streams_per_gpu": streams, "batch_event_size": args.batch, "stream_kind": args.kind, "frame": [H, W],
+            "leak": LEAK, "alpha": ALPHA, "preroll_steps": args.preroll,
+            "l2": "inputs larger than L2: %.1f GB of stream state per GPU is swept every step (L2 = 126 MB)" % (streams * 10.2e-3)}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(net, sites_per_step, nz_fraction, streams, batch):
+    """SURVEY 8(d) / BASELINE.md section 4 per step over all streams, with the leak term stated for what
+    the algorithm needs: A is read everywhere (4 B/elem), F is read and written only where A != 0."""
+    shapes = net.shapes()
+    e_conv = sum(c * h * w for nm, (c, h, w) in zip(net.names, shapes) if "conv" in nm)
+    leak = streams * e_conv * (4 + 8 * nz_fraction)
+    surface = streams * 2 * 8 * H * W
+    ev = streams * 12 * batch
+    conv = pool = 0.0
+    for i, nm in enumerate(net.names):
+        c, h, w = shapes[i]
+        n = float(sites_per_step[i])
+        if "conv" in nm:
+            cin, hin, win = shapes[i - 1]
+            k = net.infos[i].k_h * net.infos[i].k_w
+            conv += n * 8 * c + min(k * n, streams * hin * win) * 8 * cin
+        elif "pool" in nm:
+            pool += n * c * 36
+    return {"leak_sweep": leak, "surface": surface, "conv": conv, "pool": pool, "events": ev,
+            "total": leak + surface + conv + pool + ev}
+
+
+def native_arm(args):
+    import torch
+    import torch.distributed as dist
+    import async_ev_cnn_b200 as P
+    from async_ev_cnn_b200.engine import EventNetCuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:        # before CUDA is touched in this process
+        rate, cores, st, secs = run_cpu_processes(args, fixed_steps=0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d cores x 1 stream each, %.0f s timed per core after %d pre-roll steps (%d..%d steps of %d events, %s stream)" % (
+                   cores, args.cpu_seconds, args.preroll, min(st), max(st), args.batch, args.kind)}
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    S, B, K, Wm = args.streams, args.batch, args.steps, max(args.warmup, 3)
+    n_e2e = K
+    n_steps = args.preroll + Wm + 2 * K + 2 + n_e2e
+
+    wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
+    net = EventNetCuda(H, W, P.EFCN_LAYERS, wts, LEAK, ALPHA, "SAME", n_streams=S, device=local, max_events_per_step=max(2048, B))
+    ev_np = P.synthetic_events(args.kind, S, n_steps, B, H, W, seed=100 + rank)        # [S, steps, B, 3]
+    ev_np = np.ascontiguousarray(ev_np.transpose(1, 0, 2, 3)).reshape(n_steps, S * B, 3)   # per step: streams packed
+    off_np = (np.arange(S + 1, dtype=np.int64) * B).astype(np.int32)
+    ev_dev = torch.from_numpy(ev_np).cuda()
+    off_dev = torch.from_numpy(off_np).cuda()
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    def gpu_step(t):
+        net.step_device(ev_dev[t].data_ptr(), off_dev.data_ptr(), S * B, sh)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 0
+    for _ in range(args.preroll + Wm):
+        gpu_step(t)
+        t += 1
+    # ---- timed region: device-resident inputs, CUDA events on the launching stream
+    launches0 = net.launch_count()
+    net.counters(reset=True)
+    barrier()
+    sampler = ClockSampler(local)
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(K):
+        gpu_step(t)
+        t += 1
+    e1.record(stream)
+    barrier()
+    w1 = time.perf_counter()
+    clocks = sampler.stop(w0, w1)
+    ms_total = e0.elapsed_time(e1)
+    launches = net.launch_count() - launches0
+    sites, _ = net.counters(reset=True)
+    sites_per_step = sites.astype(np.float64) / K
+    if world > 1:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    value = world * S * B * K / (ms_total * 1e-3)
+
+    # ---- per-kernel durations inside the real step (events after every launch), same K steps again
+    nz_frac, _ = net.nonzero_rate_fraction()
+    net.profile(True)
+    for _ in range(K):
+        gpu_step(t)
+        t += 1
+    prof, psteps = net.read_profile()
+    net.profile(False)
+    step_ms_prof = sum(prof.values())
+    by_kernel = {}
+    for name, ms in prof.items():
+        key = name.split(".")[-1] if "." in name else name
+        key = {"frontier": "frontier_bitmaps", "eval": "site_eval"}.get(key, key)
+        if key == "site_eval":
+            key = "conv_eval" if "conv" in name else "pool_eval"
+        by_kernel[key] = by_kernel.get(key, 0.0) + ms
+    ab = algorithmic_bytes(net, sites_per_step, nz_frac, S, B)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sweep_ms = prof.get("leak_sweep", 0.0)
+    achieved = ab["leak_sweep"] / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_leak_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab["leak_sweep"], "kernel_ms": sweep_ms,
+                "kernel_share_of_step": sweep_ms / step_ms_prof if step_ms_prof else None,
+                "nonzero_rate_fraction": nz_frac,
+                "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms_total / K * 1e-3) / 1e9,
+                               "frac": ab["total"] / (ms_total / K * 1e-3) / 1e9 / peak},
+                "ms_by_kernel": {k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
+                "ms_by_launch": {k: round(v, 4) for k, v in prof.items()},
+                "sites_per_step_per_stream": {nm: round(float(sites_per_step[i]) / S, 1) for i, nm in enumerate(net.names) if i}}
+
+    # ---- end to end through the public host API: pinned host events in, head out, every step
+    ev_host = torch.from_numpy(ev_np[t:t + n_e2e]).pin_memory()
+    off_host = torch.from_numpy(off_np).pin_memory()
+    head_host = torch.empty((S,) + net.head_shape, dtype=torch.float32).pin_memory()
+    evh, offh, headh = ev_host.numpy(), off_host.numpy(), head_host.numpy()
+    net.step_packed(evh[0], offh, out=headh, cuda_stream=sh)       # warm the path (allocates the staging buffer)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(1, n_e2e):
+        net.step_packed(evh[i], offh, out=headh, cuda_stream=sh)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * S * B * (n_e2e - 1) / e2e_s
+    checksum = float(np.abs(headh).sum())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, S),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(evh[0].nbytes + offh.nbytes),
+                    "d2h_bytes_per_step": int(headh.nbytes + 4), "ms_per_step": 1e3 * e2e_s / (n_e2e - 1), "head_abs_sum": checksum},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "state_bytes_per_stream": net.state_bytes_per_stream(), "device_bytes": net.device_bytes(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    net.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.cpu_worker is not None:
+        cpu_worker(args)
+    elif args.impl == "reference":
+        reference_arm(args)
+    else:
+        native_arm(args)
+
+
+if __name__ == "__main__":
+    main()

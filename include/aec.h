@@ -188,6 +188,22 @@ int aec_net_read_step_info(aec_net *net, double *delta_out, uint8_t *active_out)
 int aec_net_read_counters(aec_net *net, unsigned long long *sites, int n_layers, unsigned long long *steps,
                           int reset);
 
+/*
+ * Per-launch timing inside the real step.  While enabled, aec_net_step_device/_host record a CUDA
+ * event on the launching stream after every kernel launch and synchronise at the end of each step;
+ * slot i of aec_net_read_profile() is the accumulated milliseconds of the i-th launch of a step
+ * (order: surface, leak sweep, then per layer frontier + evaluation, head).  Returns the number of
+ * slots.  Enabling/disabling clears the accumulators.
+ */
+int aec_net_profile(aec_net *net, int enable);
+int aec_net_read_profile(aec_net *net, double *ms_per_slot, int n_slots, unsigned long long *steps);
+
+/*
+ * Measurement helper: counts the 16-byte groups of the conv leak-rate maps that hold a non-zero
+ * rate (for which the leak sweep must read and write F) and the total number of groups.  Synchronises.
+ */
+int aec_net_count_nonzero_rate_groups(aec_net *net, unsigned long long *nz_groups, unsigned long long *total_groups);
+
 /* Number of kernels this library has launched since creation of `net` (for bench `gpu_launches`). */
 unsigned long long aec_net_launch_count(const aec_net *net);
 

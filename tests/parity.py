@@ -93,9 +93,40 @@ def assert_close_digest(got, want, exact, what):
                                    err_msg=what)
 
 
+class Mismatch:
+    """Counts the disagreements a random-float net is allowed to have (GEMM rounding decides exact or
+    near ties differently from the oracle's BLAS: SURVEY 'frontier bit-exactness vs non-reproducible
+    GEMM').  Exact nets never touch this: they are held to bit-equality."""
+
+    def __init__(self):
+        self.front_sites = 0      # frontier bits that differ
+        self.front_total = 0
+        self.idx_entries = 0.0    # argmax disagreements (estimated from digests when only those exist)
+        self.idx_total = 0
+        self.flag_windows = 0
+        self.flag_total = 0
+
+    def rates(self):
+        return (self.front_sites / max(1, self.front_total), self.idx_entries / max(1, self.idx_total),
+                self.flag_windows / max(1, self.flag_total))
+
+    def check(self, front_rate=2e-3, idx_rate=2e-4, flag_rate=5e-3):
+        fr, ir, gr = self.rates()
+        assert fr <= front_rate, "frontier disagreement rate %.2e > %.0e" % (fr, front_rate)
+        assert ir <= idx_rate, "argmax disagreement rate %.2e > %.0e" % (ir, idx_rate)
+        assert gr <= flag_rate, "recompute-flag disagreement rate %.2e > %.0e" % (gr, flag_rate)
+
+    def __repr__(self):
+        return "Mismatch(frontier %d/%d, argmax %.0f/%d, flags %d/%d)" % (
+            self.front_sites, self.front_total, self.idx_entries, self.idx_total, self.flag_windows, self.flag_total)
+
+
 def replay_golden(adapter, g, exact, steps=None, check_init=True):
-    """Feeds the fixture's events to `adapter` step by step and checks everything the fixture holds."""
+    """Feeds the fixture's events to `adapter` step by step and checks everything the fixture holds.
+    exact=True: everything bit-equal.  exact=False: float maps within FLOAT_RTOL; integer state may
+    disagree only at the (counted, bounded) rate of Mismatch.check().  Returns the Mismatch."""
     names = g.names
+    mm = Mismatch()
     assert list(adapter.names) == names
     if check_init:
         for i, nm in enumerate(names):
@@ -112,9 +143,12 @@ def replay_golden(adapter, g, exact, steps=None, check_init=True):
         assert adapter.delta() == g.z["delta"][s], "step %d: delta_leak %r vs %r" % (s, adapter.delta(), g.z["delta"][s])
         for i, nm in enumerate(names):
             got, want = adapter.frontier(i), g.front(i, s)
+            mm.front_total += int(want.sum())
             if not np.array_equal(got, want):
-                raise AssertionError("step %d layer %s: frontier differs: %d extra, %d missing (want %d sites)" % (
-                    s, nm, int((got & ~want).sum()), int((~got & want).sum()), int(want.sum())))
+                if exact:
+                    raise AssertionError("step %d layer %s: frontier differs: %d extra, %d missing (want %d sites)" % (
+                        s, nm, int((got & ~want).sum()), int((~got & want).sum()), int(want.sum())))
+                mm.front_sites += int((got ^ want).sum())
         assert_close_map(head, g.z["heads"][s], exact, "step %d head" % s)
         full = s in g.full_steps
         fi = g.full_steps.index(s) if full else -1
@@ -131,11 +165,27 @@ def replay_golden(adapter, g, exact, steps=None, check_init=True):
                     assert_close_map(st["F"], g.z["F_%s" % nm][fi], exact, "step %d F %s" % (s, nm))
                     assert_close_map(st["A"], g.z["A_%s" % nm][fi], exact, "step %d A %s" % (s, nm))
             else:
-                assert int(st["flags"].sum()) == int(g.z["flagcnt_%s" % nm][s]), "step %d flag count %s" % (s, nm)
-                assert np.array_equal(digest(st["idx"]), g.z["dgI_%s" % nm][s]), "step %d argmax digest %s" % (s, nm)
+                nflag, wflag = int(st["flags"].sum()), int(g.z["flagcnt_%s" % nm][s])
+                dg, wdg = digest(st["idx"]), g.z["dgI_%s" % nm][s]
+                mm.flag_total += st["flags"].size
+                mm.idx_total += st["idx"].size
+                if exact:
+                    assert nflag == wflag, "step %d flag count %s" % (s, nm)
+                    assert np.array_equal(dg, wdg), "step %d argmax digest %s" % (s, nm)
+                else:
+                    mm.flag_windows += abs(nflag - wflag)
+                    mm.idx_entries += abs(dg[0] - wdg[0])          # lower bound on the number of flipped entries
                 if full and "idx_%s" % nm in g.z:
-                    assert np.array_equal(st["idx"], g.z["idx_%s" % nm][fi]), "step %d argmax %s" % (s, nm)
-                    assert np.array_equal(st["flags"], g.z["flags_%s" % nm][fi].astype(bool)), "step %d flags %s" % (s, nm)
+                    wi, wf = g.z["idx_%s" % nm][fi], g.z["flags_%s" % nm][fi].astype(bool)
+                    if exact:
+                        assert np.array_equal(st["idx"], wi), "step %d argmax %s" % (s, nm)
+                        assert np.array_equal(st["flags"], wf), "step %d flags %s" % (s, nm)
+                    else:
+                        mm.idx_entries += int((st["idx"] != wi).sum())
+                        mm.flag_windows += int((st["flags"] != wf).sum())
+    if not exact:
+        mm.check()
+    return mm
 
 
 class OracleAdapter:
@@ -163,39 +213,57 @@ class OracleAdapter:
         return {"idx": layer.idx.reshape(layer.shape), "flags": layer.flags}
 
 
-def compare_live(impl, oracle, event_batches, exact, tolerate_near_zero=True):
+def compare_live(impl, oracle, event_batches, exact):
     """Steps `impl` and the live `oracle` adapter together over the same batches.
 
-    Frontier sets must be equal.  For non-exact (random-float) nets a mismatch is tolerated only if
-    it is explained by a sign decision on a value within 1e-5 of the map scale in the oracle (GEMM
-    rounding; SURVEY hard part 'frontier bit-exactness vs non-reproducible GEMM') - and is counted.
-    Returns the number of tolerated sites."""
-    tolerated = 0
+    exact=True: everything bit-equal.  exact=False: float maps within FLOAT_RTOL; every argmax
+    disagreement must be EXPLAINED by the oracle's own values - the two candidates' pre-activation
+    values differ by <= 1e-5 of the map scale (a tie decided by GEMM rounding) - and frontier / flag
+    disagreements are counted and bounded (Mismatch.check).  Returns the Mismatch."""
+    mm = Mismatch()
     for s, ev in enumerate(event_batches):
         h0 = oracle.step(ev)
         h1 = impl.step(ev)
         assert impl.delta() == oracle.delta(), "step %d delta" % s
+        prev_F = None
         for i, nm in enumerate(oracle.names):
             got, want = impl.frontier(i), oracle.frontier(i)
+            mm.front_total += int(want.sum())
             if not np.array_equal(got, want):
-                if exact or not tolerate_near_zero:
+                if exact:
                     raise AssertionError("step %d layer %s frontier: %d extra %d missing" % (
                         s, nm, int((got & ~want).sum()), int((~got & want).sum())))
-                tolerated += int((got ^ want).sum())
+                mm.front_sites += int((got ^ want).sum())
             so, si = oracle.state(i), impl.state(i)
-            for key in so:
-                if key in ("idx", "flags"):
-                    if exact:
-                        assert np.array_equal(si[key], so[key]), "step %d %s %s" % (s, nm, key)
-                    else:
-                        frac = float(np.mean(np.asarray(si[key]) != np.asarray(so[key])))
-                        assert frac < 1e-3, "step %d %s %s differs at %.2e of entries" % (s, nm, key, frac)
-                elif key == "S":
-                    assert np.array_equal(si[key], so[key]), "step %d surface" % s
+            if "S" in so:
+                assert np.array_equal(si["S"], so["S"]), "step %d surface" % s
+            elif "F" in so:
+                assert_close_map(si["F"], so["F"], exact, "step %d %s F" % (s, nm))
+                assert_close_map(si["A"], so["A"], exact, "step %d %s A" % (s, nm))
+                prev_F = so["F"]
+            else:
+                mm.idx_total += so["idx"].size
+                mm.flag_total += so["flags"].size
+                if exact:
+                    assert np.array_equal(si["idx"], so["idx"]), "step %d %s argmax" % (s, nm)
+                    assert np.array_equal(si["flags"], so["flags"]), "step %d %s flags" % (s, nm)
                 else:
-                    assert_close_map(si[key], so[key], exact, "step %d %s %s" % (s, nm, key))
+                    diff = np.argwhere(si["idx"] != so["idx"])
+                    mm.idx_entries += len(diff)
+                    mm.flag_windows += int((si["flags"] != so["flags"]).sum())
+                    if len(diff) and prev_F is not None:      # 2x2/stride-2 pools: explain each flip
+                        k = int(round((prev_F.shape[1] / so["idx"].shape[1])))
+                        scale = float(np.abs(prev_F).max())
+                        for c, y, x in diff:
+                            a, b = int(si["idx"][c, y, x]), int(so["idx"][c, y, x])
+                            fa = prev_F[c, y * k + a // k, x * k + a % k]
+                            fb = prev_F[c, y * k + b // k, x * k + b % k]
+                            assert abs(float(fa) - float(fb)) <= 1e-5 * scale, (
+                                "step %d %s argmax flip at %s is not a near tie: %r vs %r" % (s, nm, (c, y, x), fa, fb))
         assert_close_map(h1, h0, exact, "step %d head" % s)
-    return tolerated
+    if not exact:
+        mm.check()
+    return mm
 
 
 def golden_path(name):
