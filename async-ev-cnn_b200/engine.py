@@ -36,27 +36,47 @@ class EventNetCuda:
 
     def __init__(self, height, width, layers, weights, leak, alpha=0.1, padding="SAME", n_streams=1, device=0,
                  max_events_per_step=0):
+        if padding not in ("SAME", "VALID"):
+            raise ValueError("'padding' must be either 'SAME' or 'VALID', but %s has been provided." % padding)
+        spec = []
+        for name, size in parse_layers(layers).items():
+            if "conv" in name:
+                spec.append(("conv", name, weights["w_" + name], weights["b_" + name], alpha, padding))
+            elif "pool" in name:
+                spec.append(("pool", name, int(size[0]), int(size[1]), int(size[0])))
+            else:
+                raise NotImplementedError("non-event layer %r (the EFCN configs have none)" % name)
+        self._build(height, width, leak, spec, n_streams, device, max_events_per_step)
+
+    @classmethod
+    def from_spec(cls, height, width, leak, spec, n_streams=1, device=0, max_events_per_step=0):
+        """spec: list of ("conv", name, kernel_hwio, bias, alpha, padding) | ("pool", name, kh, kw, stride)."""
+        self = cls.__new__(cls)
+        self._build(height, width, leak, spec, n_streams, device, max_events_per_step)
+        return self
+
+    def _build(self, height, width, leak, spec, n_streams, device, max_events_per_step):
         self._lib = N.lib()
         self._h = ctypes.c_void_p()
         self.height, self.width = int(height), int(width)
         self.n_streams = int(n_streams)
-        self.leak, self.alpha = float(leak), float(alpha)
+        self.leak = float(leak)
         N.check(self._lib.aec_net_create(ctypes.byref(self._h), int(device), self.n_streams, self.height, self.width,
                                          self.leak, int(max_events_per_step)))
         self.names = ["intgr"]
-        if padding not in ("SAME", "VALID"):
-            raise ValueError("'padding' must be either 'SAME' or 'VALID', but %s has been provided." % padding)
-        pad = N.AEC_PAD_SAME if padding == "SAME" else N.AEC_PAD_VALID
-        for name, size in parse_layers(layers).items():
-            if "conv" in name:
-                w = np.ascontiguousarray(weights["w_" + name], dtype=np.float32)
-                b = np.ascontiguousarray(weights["b_" + name], dtype=np.float32)
+        for item in spec:
+            if item[0] == "conv":
+                _, name, w, b, alpha, padding = item
+                if padding not in ("SAME", "VALID"):
+                    raise ValueError("'padding' must be either 'SAME' or 'VALID', but %s has been provided." % padding)
+                w = np.ascontiguousarray(w, dtype=np.float32)
+                b = np.ascontiguousarray(b, dtype=np.float32).reshape(-1)
                 kh, kw, ci, co = w.shape
-                N.check(self._lib.aec_net_add_conv(self._h, kh, kw, ci, co, _ptr(w), _ptr(b), 1, self.alpha, pad))
-            elif "pool" in name:
-                N.check(self._lib.aec_net_add_pool(self._h, int(size[0]), int(size[1]), int(size[0])))
+                N.check(self._lib.aec_net_add_conv(self._h, kh, kw, ci, co, _ptr(w), _ptr(b), 1, float(alpha),
+                                                   N.AEC_PAD_SAME if padding == "SAME" else N.AEC_PAD_VALID))
             else:
-                raise NotImplementedError("non-event layer %r (the EFCN configs have none)" % name)
+                _, name, kh, kw, stride = item
+                N.check(self._lib.aec_net_add_pool(self._h, int(kh), int(kw), int(stride)))
             self.names.append(name)
         N.check(self._lib.aec_net_finalize(self._h))
         self.infos = []
