@@ -5,11 +5,13 @@
 // fallback: every compute entry point launches sm_100a kernels or fails.
 #include "../../include/aec.h"
 #include "aec_kernels.cuh"
+#include "aec_tc.cuh"
 
 #include <algorithm>
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +53,12 @@ struct HostLayer {
     uint8_t *idx = nullptr, *initIdx = nullptr;
     uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr;
     float *wgt = nullptr, *bias = nullptr;
+    // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
+    bool tc = false;
+    int KB = 0, Ntile = 0, n_tiles = 0, stages = 0, tmem_cols = 0, tc_blocks = 0;
+    size_t tc_smem = 0;
+    std::vector<float> h_wimg;
+    float *wimg = nullptr;
 };
 
 struct aec_net {
@@ -148,6 +156,54 @@ static void same_pad(int size, int k, int stride, int *before)
     *before = total / 2;
 }
 
+// The gathered GEMM runs on the tensor cores (aec_tc.cuh) when the previous layer is a conv or pool
+// layer with a multiple of 4 channels (16-byte gathers); the first conv (Cin = 1, K = kh*kw, read
+// from the float64 surface) is a 9-term stencil and stays on the SIMT kernel.  AEC_CONV_PATH=simt
+// forces the SIMT kernel everywhere (A/B measurements only).
+static void split_tf32_host(float x, float *hi, float *lo)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    memcpy(hi, &u, 4);
+    *lo = x - *hi;
+}
+
+static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_hwio)
+{
+    const char *force = getenv("AEC_CONV_PATH");
+    l.tc = prev_is_map && (l.Cin % 4 == 0) && !(force && strcmp(force, "simt") == 0);
+    if (!l.tc) return;
+    const int n16 = (l.C + 15) / 16 * 16;
+    l.n_tiles = (n16 + 255) / 256;
+    l.Ntile = ((n16 + l.n_tiles - 1) / l.n_tiles + 15) / 16 * 16;
+    l.KB = (l.K + tc::kBlockK - 1) / tc::kBlockK;
+    l.tmem_cols = 32;
+    while (l.tmem_cols < l.Ntile) l.tmem_cols <<= 1;
+    const size_t stage = 2 * (size_t)tc::kATileBytes + 2 * (size_t)l.Ntile * 128;
+    const size_t two_per_sm = 110 * 1024, one_per_sm = 224 * 1024;
+    size_t st = 2 * stage <= two_per_sm ? two_per_sm / stage : one_per_sm / stage;
+    l.stages = (int)std::min<size_t>(std::max<size_t>(st, 1), 4);
+    l.stages = std::min(l.stages, std::max(l.KB, 1));
+    l.tc_smem = (size_t)l.stages * stage + 1024;
+    if ((size_t)l.h_b.size() < (size_t)l.Ntile * l.n_tiles) l.h_b.resize((size_t)l.Ntile * l.n_tiles, 0.f);
+    l.h_wimg.assign((size_t)l.n_tiles * l.KB * 2 * l.Ntile * tc::kBlockK, 0.f);
+    for (int nt = 0; nt < l.n_tiles; ++nt)
+        for (int kb = 0; kb < l.KB; ++kb)
+            for (int r = 0; r < l.Ntile; ++r)
+                for (int j = 0; j < 8; ++j)
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = kb * tc::kBlockK + 4 * j + e, col = nt * l.Ntile + r;
+                        const float w = (k < l.K && col < l.C) ? kernel_hwio[(size_t)k * l.C + col] : 0.f;
+                        float hi, lo;
+                        split_tf32_host(w, &hi, &lo);
+                        const size_t base = ((size_t)(nt * l.KB + kb) * 2) * l.Ntile * tc::kBlockK;
+                        const size_t off = (size_t)r * tc::kBlockK + (size_t)((j ^ (r & 7)) * 4) + e;
+                        l.h_wimg[base + off] = hi;
+                        l.h_wimg[base + (size_t)l.Ntile * tc::kBlockK + off] = lo;
+                    }
+}
+
 extern "C" int aec_net_add_conv(aec_net *n, int k_h, int k_w, int c_in, int c_out, const float *kernel_hwio,
                                 const float *bias, int stride, float alpha, int padding)
 {
@@ -187,6 +243,7 @@ extern "C" int aec_net_add_conv(aec_net *n, int k_h, int k_w, int c_in, int c_ou
     for (int k = 0; k < l.K; ++k)          // HWIO flattened is already [k = (ky,kx,ci)][co]
         for (int c = 0; c < c_out; ++c) l.h_w[(size_t)k * l.Npad + c] = kernel_hwio[(size_t)k * c_out + c];
     for (int c = 0; c < c_out; ++c) l.h_b[c] = bias[c];
+    build_tc_image(l, p.type != AEC_LAYER_INTEGRATION, kernel_hwio);
     n->L.push_back(std::move(l));
     return (int)n->L.size() - 1;
 }
@@ -317,9 +374,25 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
     return launch_check(n, "k_leak_sweep");
 }
 
+static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
+{
+    HostLayer &l = n->L[li];
+    tc::TcParams p;
+    p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
+    p.src = make_src(n, li - 1);
+    p.wimg = l.wimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.Ntile = l.Ntile; p.n_tiles = l.n_tiles;
+    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.stages = l.stages; p.tmem_cols = l.tmem_cols;
+    if (p.src.kind == 1) tc::k_conv_eval_tc<1><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    else tc::k_conv_eval_tc<2><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    int rc = launch_check(n, "k_conv_eval_tc");
+    return rc ? rc : prof_mark(n, st);
+}
+
 static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
 {
     HostLayer &l = n->L[li];
+    if (l.tc) return run_conv_eval_tc(n, li, st);
     ConvEvalParams p;
     p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.src = make_src(n, li - 1);
@@ -452,6 +525,11 @@ extern "C" int aec_net_finalize(aec_net *n)
             CU(cudaMemcpy(l.wgt, l.h_w.data(), l.h_w.size() * 4, cudaMemcpyHostToDevice));
             CU(cudaMemcpy(l.bias, l.h_b.data(), l.h_b.size() * 4, cudaMemcpyHostToDevice));
             l.h_w.clear(); l.h_w.shrink_to_fit();
+            if (l.tc) {
+                if ((rc = dev_alloc(n, &l.wimg, l.h_wimg.size(), false))) return rc;
+                CU(cudaMemcpy(l.wimg, l.h_wimg.data(), l.h_wimg.size() * 4, cudaMemcpyHostToDevice));
+                l.h_wimg.clear(); l.h_wimg.shrink_to_fit();
+            }
         } else if (l.type == AEC_LAYER_POOL) {
             if ((rc = dev_alloc(n, &l.idx, S * l.fstride, true))) return rc;
             if ((rc = dev_alloc(n, &l.flags, S * bm, true))) return rc;
@@ -500,6 +578,25 @@ extern "C" int aec_net_finalize(aec_net *n)
         CU(cudaFuncSetAttribute(k_conv_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fc, 48 * 1024)));
         CU(cudaFuncSetAttribute(k_pool_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fp, 48 * 1024)));
         int b = 0;
+        size_t tc_max[3] = {0, 0, 0};
+        for (size_t i = 1; i < n->L.size(); ++i)
+            if (n->L[i].type == AEC_LAYER_CONV && n->L[i].tc) {
+                const int kind = n->L[i - 1].type == AEC_LAYER_CONV ? 1 : 2;
+                tc_max[kind] = std::max(tc_max[kind], n->L[i].tc_smem);
+            }
+        if (tc_max[1]) CU(cudaFuncSetAttribute(tc::k_conv_eval_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max[1]));
+        if (tc_max[2]) CU(cudaFuncSetAttribute(tc::k_conv_eval_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max[2]));
+        for (size_t i = 1; i < n->L.size(); ++i) {
+            HostLayer &l = n->L[i];
+            if (l.type != AEC_LAYER_CONV || !l.tc) continue;
+            if (n->L[i - 1].type == AEC_LAYER_CONV)
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, tc::k_conv_eval_tc<1>, tc::kTcThreads, l.tc_smem));
+            else
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, tc::k_conv_eval_tc<2>, tc::kTcThreads, l.tc_smem));
+            // TMEM: 512 columns per SM shared by the resident CTAs
+            b = std::min(std::max(1, b), 512 / l.tmem_cols);
+            l.tc_blocks = b * n->num_sms;
+        }
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));
         n->conv_eval_blocks[0] = std::max(1, b) * n->num_sms;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<32, 4, 4, 16>, kThreads, 0));
