@@ -51,11 +51,12 @@ struct HostLayer {
     std::vector<float> h_w, h_b;   // padded host copies until finalize
     float *F = nullptr, *A = nullptr, *initF = nullptr;
     uint8_t *idx = nullptr, *initIdx = nullptr;
+    float *Fp = nullptr, *Ap = nullptr, *initFp = nullptr;   // pool: copy of the conv maps at the argmax
     uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr;
     float *wgt = nullptr, *bias = nullptr;
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
     bool tc = false;
-    int KB = 0, Ntile = 0, n_tiles = 0, stages = 0, tmem_cols = 0, tc_blocks = 0;
+    int KB = 0, Ntile = 0, n_tiles = 0, a_stages = 0, b_stages = 0, n_acc = 1, tc_blocks = 0;
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
@@ -80,7 +81,7 @@ struct aec_net {
     int32_t *ev_dev = nullptr, *off_dev = nullptr;
     size_t ev_cap = 0;
     int num_sms = 148;
-    int sweep_chunks = 0;
+    int sweep_chunks = 0, sweep_nconv = 0, sweep_conv_chunks = 0;
     SweepParams sweep_all;
     unsigned long long launches = 0, steps = 0;
     int conv_eval_blocks[4] = {0, 0, 0, 0};
@@ -175,17 +176,14 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
     l.tc = prev_is_map && (l.Cin % 4 == 0) && !(force && strcmp(force, "simt") == 0);
     if (!l.tc) return;
     const int n16 = (l.C + 15) / 16 * 16;
-    l.n_tiles = (n16 + 255) / 256;
+    l.n_tiles = (n16 + tc::kMaxNtile - 1) / tc::kMaxNtile;
     l.Ntile = ((n16 + l.n_tiles - 1) / l.n_tiles + 15) / 16 * 16;
     l.KB = (l.K + tc::kBlockK - 1) / tc::kBlockK;
-    l.tmem_cols = 32;
-    while (l.tmem_cols < l.Ntile) l.tmem_cols <<= 1;
-    const size_t stage = 2 * (size_t)tc::kATileBytes + 2 * (size_t)l.Ntile * 128;
-    const size_t two_per_sm = 110 * 1024, one_per_sm = 224 * 1024;
-    size_t st = 2 * stage <= two_per_sm ? two_per_sm / stage : one_per_sm / stage;
-    l.stages = (int)std::min<size_t>(std::max<size_t>(st, 1), 4);
-    l.stages = std::min(l.stages, std::max(l.KB, 1));
-    l.tc_smem = (size_t)l.stages * stage + 1024;
+    l.n_acc = 2 * tc::kMT * l.Ntile <= 512 ? 2 : 1;
+    l.a_stages = 4;
+    const size_t b_stage = 2 * (size_t)l.Ntile * 128, budget = 216 * 1024;
+    l.b_stages = (int)std::min<size_t>(tc::kMaxStages, std::max<size_t>(2, (budget - (size_t)l.a_stages * tc::kAStageBytes) / b_stage));
+    l.tc_smem = (size_t)l.a_stages * tc::kAStageBytes + (size_t)l.b_stages * b_stage + 1024;
     if ((size_t)l.h_b.size() < (size_t)l.Ntile * l.n_tiles) l.h_b.resize((size_t)l.Ntile * l.n_tiles, 0.f);
     l.h_wimg.assign((size_t)l.n_tiles * l.KB * 2 * l.Ntile * tc::kBlockK, 0.f);
     for (int nt = 0; nt < l.n_tiles; ++nt)
@@ -288,10 +286,8 @@ static Src make_src(const aec_net *n, int li)
         q.kind = 1;
         q.F = l.F; q.A = l.A; q.fstride = l.fstride; q.alpha = l.alpha;
     } else {
-        const HostLayer &c = n->L[li - 1];
-        q.kind = 2;
-        q.F = c.F; q.A = c.A; q.fstride = c.fstride; q.alpha = c.alpha; q.cW = c.W;
-        q.idx = l.idx; q.istride = l.fstride; q.pkw = l.kw; q.pstride = l.stride;
+        q.kind = 1;
+        q.F = l.Fp; q.A = l.Ap; q.fstride = l.fstride; q.alpha = n->L[li - 1].alpha;
     }
     return q;
 }
@@ -351,7 +347,9 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
 
 static void fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0)
 {
-    o.F = l.F; o.A = l.A; o.signchg = l.signchg; o.fstride = l.fstride;
+    if (l.type == AEC_LAYER_POOL) { o.F = l.Fp; o.A = l.Ap; o.signchg = nullptr; }
+    else { o.F = l.F; o.A = l.A; o.signchg = l.signchg; }
+    o.fstride = l.fstride;
     o.n4 = (int)(l.fstride / 4); o.chunk0 = chunk0;
     o.C = l.C; o.W = l.W; o.Ww = l.Ww; o.HWw = l.H * l.Ww;
 }
@@ -377,14 +375,16 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
 static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
 {
     HostLayer &l = n->L[li];
+    const Src src = make_src(n, li - 1);
     tc::TcParams p;
     p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
-    p.src = make_src(n, li - 1);
+    p.srcF = src.F; p.srcA = src.A; p.src_stride = src.fstride; p.alpha = src.alpha;
+    p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
     p.wimg = l.wimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.Ntile = l.Ntile; p.n_tiles = l.n_tiles;
-    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.stages = l.stages; p.tmem_cols = l.tmem_cols;
-    if (p.src.kind == 1) tc::k_conv_eval_tc<1><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
-    else tc::k_conv_eval_tc<2><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+    p.a_stages = l.a_stages; p.b_stages = l.b_stages; p.n_acc = l.n_acc;
+    tc::k_conv_eval_tc<<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st);
 }
@@ -416,9 +416,10 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     PoolEvalParams p;
     p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.F = c.F; p.A = c.A; p.fstride = c.fstride; p.alpha = c.alpha; p.cW = c.W;
-    p.idx = l.idx; p.istride = l.fstride; p.flags = l.flags;
+    p.idx = l.idx; p.Fp = l.Fp; p.Ap = l.Ap; p.pstride = l.fstride; p.flags = l.flags;
     p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
-    k_pool_eval<<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    if (l.C % 4 == 0) k_pool_eval<4><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    else k_pool_eval<1><<<n->num_sms * 8, kThreads, 0, st>>>(p);
     int rc = launch_check(n, "k_pool_eval");
     return rc ? rc : prof_mark(n, st);
 }
@@ -441,6 +442,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
         if ((rc = prof_mark(n, st))) return rc;
         return run_conv_eval(n, li, st);
     }
+    if (with_sweep && (rc = run_sweep(n, li, st))) return rc;     // the (Fp, Ap) copy leaks before it is refreshed
     PoolFrontParams p;
     p.prev_front = pv.front; p.front = l.front; p.flags = l.flags; p.active = n->active;
     p.sites = n->sites; p.counter = n->counts + li;
@@ -494,6 +496,8 @@ static int reset_streams(aec_net *n, const uint8_t *mask_dev, cudaStream_t st)
         } else if (l.type == AEC_LAYER_POOL) {
             if ((rc = broadcast(n, l.idx, l.initIdx, l.fstride, l.fstride, mask_dev, st))) return rc;
             if ((rc = broadcast(n, l.flags, nullptr, bm, bm, mask_dev, st))) return rc;
+            if ((rc = broadcast(n, l.Fp, l.initFp, l.fstride * 4, l.fstride * 4, mask_dev, st))) return rc;
+            if ((rc = broadcast(n, l.Ap, nullptr, l.fstride * 4, l.fstride * 4, mask_dev, st))) return rc;
         }
     }
     return AEC_OK;
@@ -534,6 +538,9 @@ extern "C" int aec_net_finalize(aec_net *n)
             if ((rc = dev_alloc(n, &l.idx, S * l.fstride, true))) return rc;
             if ((rc = dev_alloc(n, &l.flags, S * bm, true))) return rc;
             if ((rc = dev_alloc(n, &l.initIdx, (size_t)l.fstride, false))) return rc;
+            if ((rc = dev_alloc(n, &l.Fp, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc(n, &l.Ap, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc(n, &l.initFp, (size_t)l.fstride, false))) return rc;
         }
         if (l.type != AEC_LAYER_INTEGRATION) maxHW = std::max(maxHW, (size_t)l.H * l.W);
     }
@@ -549,15 +556,18 @@ extern "C" int aec_net_finalize(aec_net *n)
     n->head_per_stream = (size_t)last.H * last.W * last.C;
     if ((rc = dev_alloc(n, &n->head, S * n->head_per_stream, true))) return rc;
 
-    // leak-sweep table over all conv layers
+    // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
     int chunk0 = 0, nc = 0;
-    for (auto &l : n->L)
-        if (l.type == AEC_LAYER_CONV) {
-            fill_sweep_layer(l, n->sweep_all.L[nc], chunk0);
-            chunk0 += (n->sweep_all.L[nc].n4 + kSweepChunk - 1) / kSweepChunk;
-            ++nc;
-        }
+    for (int pass = 0; pass < 2; ++pass) {
+        for (auto &l : n->L)
+            if (l.type == (pass == 0 ? AEC_LAYER_CONV : AEC_LAYER_POOL)) {
+                fill_sweep_layer(l, n->sweep_all.L[nc], chunk0);
+                chunk0 += (n->sweep_all.L[nc].n4 + kSweepChunk - 1) / kSweepChunk;
+                ++nc;
+            }
+        if (pass == 0) { n->sweep_nconv = nc; n->sweep_conv_chunks = chunk0; }
+    }
     n->sweep_all.n_layers = nc;
     n->sweep_all.delta = n->delta;
     n->sweep_all.active = n->active;
@@ -578,25 +588,14 @@ extern "C" int aec_net_finalize(aec_net *n)
         CU(cudaFuncSetAttribute(k_conv_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fc, 48 * 1024)));
         CU(cudaFuncSetAttribute(k_pool_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fp, 48 * 1024)));
         int b = 0;
-        size_t tc_max[3] = {0, 0, 0};
-        for (size_t i = 1; i < n->L.size(); ++i)
-            if (n->L[i].type == AEC_LAYER_CONV && n->L[i].tc) {
-                const int kind = n->L[i - 1].type == AEC_LAYER_CONV ? 1 : 2;
-                tc_max[kind] = std::max(tc_max[kind], n->L[i].tc_smem);
+        size_t tc_max = 0;
+        for (auto &l : n->L)
+            if (l.type == AEC_LAYER_CONV && l.tc) {
+                tc_max = std::max(tc_max, l.tc_smem);
+                l.tc_blocks = n->num_sms;              // persistent: one warp-specialised CTA per SM (all 512 TMEM columns)
             }
-        if (tc_max[1]) CU(cudaFuncSetAttribute(tc::k_conv_eval_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max[1]));
-        if (tc_max[2]) CU(cudaFuncSetAttribute(tc::k_conv_eval_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max[2]));
-        for (size_t i = 1; i < n->L.size(); ++i) {
-            HostLayer &l = n->L[i];
-            if (l.type != AEC_LAYER_CONV || !l.tc) continue;
-            if (n->L[i - 1].type == AEC_LAYER_CONV)
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, tc::k_conv_eval_tc<1>, tc::kTcThreads, l.tc_smem));
-            else
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, tc::k_conv_eval_tc<2>, tc::kTcThreads, l.tc_smem));
-            // TMEM: 512 columns per SM shared by the resident CTAs
-            b = std::min(std::max(1, b), 512 / l.tmem_cols);
-            l.tc_blocks = b * n->num_sms;
-        }
+        if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
+        if (tc_max) CU(cudaFuncSetAttribute(tc::k_conv_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));
         n->conv_eval_blocks[0] = std::max(1, b) * n->num_sms;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<32, 4, 4, 16>, kThreads, 0));
@@ -622,6 +621,8 @@ extern "C" int aec_net_finalize(aec_net *n)
         } else {
             if ((rc = run_pool_eval(n, (int)li, st))) return rc;
             CU(cudaMemcpyAsync(l.initIdx, l.idx, (size_t)l.fstride, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(l.initFp, l.Fp, (size_t)l.fstride * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemsetAsync(l.Ap, 0, (size_t)l.fstride * 4, st));
             CU(cudaMemsetAsync(l.flags, 0, (size_t)l.H * l.Ww * 4, st));
         }
     }
@@ -879,10 +880,12 @@ extern "C" int aec_net_count_nonzero_rate_groups(aec_net *n, unsigned long long 
     CU(cudaDeviceSynchronize());
     CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
     unsigned long long total = 0;
-    for (int i = 0; i < n->sweep_all.n_layers; ++i) total += (unsigned long long)n->sweep_all.L[i].n4 * n->S;
-    if (n->sweep_all.n_layers) {
-        dim3 grid(n->sweep_chunks, n->S);
-        k_count_nz4<<<grid, kThreads>>>(n->sweep_all, n->accum + 31);
+    for (int i = 0; i < n->sweep_nconv; ++i) total += (unsigned long long)n->sweep_all.L[i].n4 * n->S;
+    if (n->sweep_nconv) {
+        SweepParams conv_only = n->sweep_all;
+        conv_only.n_layers = n->sweep_nconv;
+        dim3 grid(n->sweep_conv_chunks, n->S);
+        k_count_nz4<<<grid, kThreads>>>(conv_only, n->accum + 31);
         int rc = launch_check(n, "k_count_nz4");
         if (rc) return rc;
     }

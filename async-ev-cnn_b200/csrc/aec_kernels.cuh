@@ -4,6 +4,11 @@
 //   surface   double [S][H*W]                     leaky integration surface (f64: SURVEY Q2)
 //   F_l, A_l  float  [S][pad4(H_l*W_l*C_l)]        conv pre-activation / leak-rate maps, CHANNEL-LAST
 //   idx_l     uint8  [S][Ho*Wo*C]                  pool argmax row (ky*kw+kx), channel-last
+//   Fp_l,Ap_l float  [S][pad4(Ho*Wo*C)]            pool layers: copy of the previous conv's F / A at the
+//                                                  stored argmax (kept equal by the leak sweep, which
+//                                                  applies the same arithmetic to the copy, and by the
+//                                                  pool evaluation, which refreshes re-evaluated windows);
+//                                                  lets every consumer gather 16-byte channel vectors
 //   flags_l   uint32 [S][Ho][ceil(Wo/32)]          pool sticky recompute bitmap
 //   front_l   uint32 [S][H_l][ceil(W_l/32)]        output-event ("frontier") bitmap of layer l
 //   signchg_l uint32 [S][H_l][ceil(W_l/32)]        conv sites whose sign flipped in the leak sweep
@@ -22,26 +27,25 @@
 namespace aec {
 
 constexpr int kThreads = 256;
-constexpr int kMaxConv = 24;
+constexpr int kMaxConv = 24;           // conv layers per network
+constexpr int kMaxSweep = 2 * kMaxConv;  // leak-sweep table: conv maps + pooled copies
 
 // ---------------------------------------------------------------------------------------------
 // What a consumer sees of its previous layer: value V = surface*layer_actfn (layer.py:77-81) and
 // rate R = conv_actfn.  kind 0: integration (V=(float)S, R=[S>0]; integration.py:33-43),
-// kind 1: conv (V=F*slope, R=A*slope, slope = F>0 ? 1 : alpha; conv2d.py:83-94),
-// kind 2: pool over a conv (the same, read through the stored argmax; maxpool.py:42-79).
+// kind 1: a channel-last (F, A) map pair: V=F*slope, R=A*slope, slope = F>0 ? 1 : alpha
+//         (conv2d.py:83-94).  For a conv layer the pair is its own state; for a pool layer it is the
+//         materialised copy of the previous conv's maps at the stored argmax, which is what
+//         maxpool.py:42-79 gathers (surface = F[argmax], conv_actfn = (A*slope)[argmax]).
 // ---------------------------------------------------------------------------------------------
 struct Src {
     int kind;
     int C, H, W;            // shape of the previous layer's output map
     const double *S;        // kind 0
     long long sstride;
-    const float *F, *A;     // kind 1/2: the underlying conv maps
+    const float *F, *A;     // kind 1
     long long fstride;
     float alpha;
-    int cW;                 // kind 2: width of the underlying conv map
-    const uint8_t *idx;     // kind 2
-    long long istride;
-    int pkw, pstride;       // kind 2: pool window width / stride
 };
 
 __device__ __forceinline__ float slope_of(float f, float alpha) { return f > 0.f ? 1.f : alpha; }
@@ -54,38 +58,25 @@ __device__ __forceinline__ void src_fetch(const Src &q, int s, int y, int x, int
         r = sv > 0.0 ? 1.f : 0.f;
         return;
     }
-    long long off;
-    if (q.kind == 1) {
-        off = ((long long)y * q.W + x) * q.C + c;
-    } else {
-        const int i = q.idx[(long long)s * q.istride + ((long long)y * q.W + x) * q.C + c];
-        off = ((long long)(y * q.pstride + i / q.pkw) * q.cW + (x * q.pstride + i % q.pkw)) * q.C + c;
-    }
-    const float f = q.F[(long long)s * q.fstride + off];
-    const float a = q.A[(long long)s * q.fstride + off];
+    const long long off = (long long)s * q.fstride + ((long long)y * q.W + x) * q.C + c;
+    const float f = q.F[off];
+    const float a = q.A[off];
     const float sl = slope_of(f, q.alpha);
     v = __fmul_rn(f, sl);
     r = __fmul_rn(a, sl);
 }
 
-// 4 consecutive channels (c % 4 == 0, C % 4 == 0).
+// 4 consecutive channels (c % 4 == 0, C % 4 == 0, kind 1).
 __device__ __forceinline__ void src_fetch4(const Src &q, int s, int y, int x, int c, float4 &v, float4 &r)
 {
-    if (q.kind == 1) {
-        const long long off = (long long)s * q.fstride + ((long long)y * q.W + x) * q.C + c;
-        const float4 f = __ldg(reinterpret_cast<const float4 *>(q.F + off));
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(q.A + off));
-        float sl;
-        sl = slope_of(f.x, q.alpha); v.x = __fmul_rn(f.x, sl); r.x = __fmul_rn(a.x, sl);
-        sl = slope_of(f.y, q.alpha); v.y = __fmul_rn(f.y, sl); r.y = __fmul_rn(a.y, sl);
-        sl = slope_of(f.z, q.alpha); v.z = __fmul_rn(f.z, sl); r.z = __fmul_rn(a.z, sl);
-        sl = slope_of(f.w, q.alpha); v.w = __fmul_rn(f.w, sl); r.w = __fmul_rn(a.w, sl);
-    } else {
-        src_fetch(q, s, y, x, c + 0, v.x, r.x);
-        src_fetch(q, s, y, x, c + 1, v.y, r.y);
-        src_fetch(q, s, y, x, c + 2, v.z, r.z);
-        src_fetch(q, s, y, x, c + 3, v.w, r.w);
-    }
+    const long long off = (long long)s * q.fstride + ((long long)y * q.W + x) * q.C + c;
+    const float4 f = __ldg(reinterpret_cast<const float4 *>(q.F + off));
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(q.A + off));
+    float sl;
+    sl = slope_of(f.x, q.alpha); v.x = __fmul_rn(f.x, sl); r.x = __fmul_rn(a.x, sl);
+    sl = slope_of(f.y, q.alpha); v.y = __fmul_rn(f.y, sl); r.y = __fmul_rn(a.y, sl);
+    sl = slope_of(f.z, q.alpha); v.z = __fmul_rn(f.z, sl); r.z = __fmul_rn(a.z, sl);
+    sl = slope_of(f.w, q.alpha); v.w = __fmul_rn(f.w, sl); r.w = __fmul_rn(a.w, sl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,7 +298,9 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
 //   F <- (float)((double)F - (double)A * delta)   [NEP-50 arithmetic of `f32 -= f32 * np.float64`]
 //   sites where sign(F >= 0) flipped in any channel are recorded in signchg.
 // Elements with A == 0 keep F bit-for-bit (x - 0 == x), so F is neither read nor written there.
-// Grid: (chunks per stream over all conv layers, S).
+// The table also holds the pool layers' (Fp, Ap) copies (signchg == nullptr): the same arithmetic on
+// the same bits keeps each copy equal to the conv element it mirrors.
+// Grid: (chunks per stream over all table entries, S).
 // ---------------------------------------------------------------------------------------------
 struct SweepLayer {
     float *F, *A;
@@ -318,7 +311,7 @@ struct SweepLayer {
     int C, W, Ww, HWw;   // HWw = H*Ww
 };
 struct SweepParams {
-    SweepLayer L[kMaxConv];
+    SweepLayer L[kMaxSweep];
     int n_layers;
     const double *delta;
     const uint8_t *active;
@@ -367,7 +360,7 @@ __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__
         F4[idx[j]] = g;
         const unsigned flips = ((f.x >= 0.f) != (g.x >= 0.f) ? 1u : 0u) | ((f.y >= 0.f) != (g.y >= 0.f) ? 2u : 0u) |
                                ((f.z >= 0.f) != (g.z >= 0.f) ? 4u : 0u) | ((f.w >= 0.f) != (g.w >= 0.f) ? 8u : 0u);
-        if (flips) {
+        if (flips && L.signchg) {
             uint32_t *sc = L.signchg + (long long)s * L.HWw;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -519,7 +512,8 @@ __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
 // K5: pool evaluation over the work list.   maxpool.py:130-151, cutils.pyx:161-177
 //   per (window, channel): argmax of F over the window rows (ascending ky*kw+kx), ties -> smaller
 //   rate R = A*slope(F), then smaller row; argmin of R (first); unstable = R[argmax] != R[argmin];
-//   idx <- argmax; flags[window] |= any-channel unstable.
+//   idx <- argmax; flags[window] |= any-channel unstable; (Fp, Ap) <- (F, A) at the argmax.
+// One thread per (window, VEC consecutive channels): VEC = 4 uses 16-byte loads/stores (C % 4 == 0).
 // ---------------------------------------------------------------------------------------------
 struct PoolEvalParams {
     const uint32_t *sites;
@@ -530,45 +524,79 @@ struct PoolEvalParams {
     float alpha;
     int cW;                       // previous conv width
     uint8_t *idx;                 // [S][H*W*C]
-    long long istride;
+    float *Fp, *Ap;               // [S][pstride] copies at the argmax
+    long long pstride;            // idx bytes == copy floats per stream
     uint32_t *flags;              // [S][H*Ww]
     int C, H, W, Ww;
     int kh, kw, stride;
 };
 
+struct PoolBest {
+    float f, r, a, rlow;
+    int row;
+};
+__device__ __forceinline__ void pool_first(PoolBest &b, float f, float a, float alpha)
+{
+    b.f = f; b.a = a; b.r = __fmul_rn(a, slope_of(f, alpha)); b.rlow = b.r; b.row = 0;
+}
+__device__ __forceinline__ void pool_next(PoolBest &b, int row, float f, float a, float alpha)
+{
+    const float r = __fmul_rn(a, slope_of(f, alpha));
+    if (f > b.f || (f == b.f && r < b.r)) { b.row = row; b.f = f; b.r = r; b.a = a; }   // cutils.pyx:166-170
+    if (r < b.rlow) b.rlow = r;                                                          // cutils.pyx:173-174
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(kThreads) k_pool_eval(PoolEvalParams p)
 {
     const int n = *p.counter;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.accum, (unsigned long long)n);
-    const long long total = (long long)n * p.C;
+    const int CG = p.C / VEC;
+    const long long total = (long long)n * CG;
     const int HW = p.H * p.W;
     for (long long wi = (long long)blockIdx.x * kThreads + threadIdx.x; wi < total; wi += (long long)gridDim.x * kThreads) {
-        const uint32_t e = p.sites[wi / p.C];
-        const int c = (int)(wi % p.C);
+        const uint32_t e = p.sites[wi / CG];
+        const int c = (int)(wi % CG) * VEC;
         const int s = (int)(e / (uint32_t)HW);
         const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
         const int oy = site / p.W, ox = site - oy * p.W;
         const float *Fb = p.F + (long long)s * p.fstride;
         const float *Ab = p.A + (long long)s * p.fstride;
-        int best = 0, low = 0;
-        float fbest = 0.f, rbest = 0.f, rlow = 0.f;
+        PoolBest best[VEC];
         int row = 0;
         for (int dy = 0; dy < p.kh; ++dy)
             for (int dx = 0; dx < p.kw; ++dx, ++row) {
                 const long long off = ((long long)(oy * p.stride + dy) * p.cW + (ox * p.stride + dx)) * p.C + c;
-                const float f = Fb[off];
-                const float r = __fmul_rn(Ab[off], slope_of(f, p.alpha));
-                if (row == 0) {
-                    fbest = f; rbest = r; rlow = r;
+                float f[VEC], a[VEC];
+                if constexpr (VEC == 4) {
+                    const float4 f4 = __ldg(reinterpret_cast<const float4 *>(Fb + off));
+                    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(Ab + off));
+                    f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
+                    a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
                 } else {
-                    if (f > fbest) { best = row; fbest = f; rbest = r; }
-                    else if (f == fbest && r < rbest) { best = row; fbest = f; rbest = r; }
-                    if (r < rlow) { low = row; rlow = r; }
+                    f[0] = Fb[off];
+                    a[0] = Ab[off];
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (row == 0) pool_first(best[v], f[v], a[v], p.alpha);
+                    else pool_next(best[v], row, f[v], a[v], p.alpha);
                 }
             }
-        (void)low;
-        p.idx[(long long)s * p.istride + (long long)site * p.C + c] = (uint8_t)best;
-        const bool unstable = rbest != rlow;
+        bool unstable = false;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) unstable |= best[v].r != best[v].rlow;      // cutils.pyx:177 (by value)
+        const long long o = (long long)s * p.pstride + (long long)site * p.C + c;
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<uchar4 *>(p.idx + o) = make_uchar4((unsigned char)best[0].row, (unsigned char)best[1].row,
+                                                                  (unsigned char)best[2].row, (unsigned char)best[3].row);
+            *reinterpret_cast<float4 *>(p.Fp + o) = make_float4(best[0].f, best[1].f, best[2].f, best[3].f);
+            *reinterpret_cast<float4 *>(p.Ap + o) = make_float4(best[0].a, best[1].a, best[2].a, best[3].a);
+        } else {
+            p.idx[o] = (uint8_t)best[0].row;
+            p.Fp[o] = best[0].f;
+            p.Ap[o] = best[0].a;
+        }
         // one atomic per (warp, window): lanes of the same window elect a leader
         const unsigned act = __activemask();
         const unsigned peers = __match_any_sync(act, e);
@@ -789,18 +817,8 @@ __global__ void __launch_bounds__(kThreads) k_layer_view(ViewParams p)
     const Src &q = p.src;
     const long long per = (long long)q.H * q.W * q.C;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < per; i += (long long)gridDim.x * kThreads) {
-        const int c = (int)(i % q.C);
-        const int site = (int)(i / q.C);
-        const int y = site / q.W, x = site - y * q.W;
-        long long off;
-        if (q.kind == 1) {
-            off = i;
-        } else {
-            const int k = q.idx[(long long)p.stream * q.istride + i];
-            off = ((long long)(y * q.pstride + k / q.pkw) * q.cW + (x * q.pstride + k % q.pkw)) * q.C + c;
-        }
-        const float f = q.F[(long long)p.stream * q.fstride + off];
-        const float a = q.A[(long long)p.stream * q.fstride + off];
+        const float f = q.F[(long long)p.stream * q.fstride + i];
+        const float a = q.A[(long long)p.stream * q.fstride + i];
         const float sl = slope_of(f, q.alpha);
         if (p.surface) p.surface[i] = f;
         if (p.layer_actfn) p.layer_actfn[i] = sl;
