@@ -52,14 +52,15 @@ struct HostLayer {
     float *F = nullptr, *A = nullptr, *initF = nullptr;
     uint8_t *idx = nullptr, *initIdx = nullptr;
     float *Fp = nullptr, *Ap = nullptr, *initFp = nullptr;   // pool: copy of the conv maps at the argmax
-    uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr;
+    uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr, *nzr = nullptr;
     float *wgt = nullptr, *bias = nullptr;
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
     bool tc = false;
-    int KB = 0, Ntile = 0, n_tiles = 0, a_stages = 0, b_stages = 0, n_acc = 1, tc_blocks = 0;
+    int KB = 0, Mrows = 0, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
+    unsigned long long *tc_timing = nullptr;   // 16 counters, used while aec_net_tc_timing is enabled
 };
 
 struct aec_net {
@@ -91,6 +92,7 @@ struct aec_net {
     std::vector<double> prof_ms;            // accumulated ms per slot
     int prof_slot = 0;
     unsigned long long prof_steps = 0;
+    bool tc_timing_on = false;
     float *view = nullptr;      // 4 x max(H*W*C) scratch for aec_net_read_view
     size_t view_elems = 0;
 };
@@ -175,30 +177,32 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
     const char *force = getenv("AEC_CONV_PATH");
     l.tc = prev_is_map && (l.Cin % 4 == 0) && !(force && strcmp(force, "simt") == 0);
     if (!l.tc) return;
-    const int n16 = (l.C + 15) / 16 * 16;
-    l.n_tiles = (n16 + tc::kMaxNtile - 1) / tc::kMaxNtile;
-    l.Ntile = ((n16 + l.n_tiles - 1) / l.n_tiles + 15) / 16 * 16;
+    const int c8 = (l.C + 7) / 8 * 8;
+    l.m_tiles = (c8 + 127) / 128;
+    l.Mrows = ((c8 + l.m_tiles - 1) / l.m_tiles + 7) / 8 * 8;      // output channels per weight tile (<= 128)
+    l.mtu = std::min(l.m_tiles, tc::kMaxMtu);
+    l.n_acc = l.mtu == 1 ? 2 : 1;
     l.KB = (l.K + tc::kBlockK - 1) / tc::kBlockK;
-    l.n_acc = 2 * tc::kMT * l.Ntile <= 512 ? 2 : 1;
-    l.a_stages = 4;
-    const size_t b_stage = 2 * (size_t)l.Ntile * 128, budget = 216 * 1024;
-    l.b_stages = (int)std::min<size_t>(tc::kMaxStages, std::max<size_t>(2, (budget - (size_t)l.a_stages * tc::kAStageBytes) / b_stage));
-    l.tc_smem = (size_t)l.a_stages * tc::kAStageBytes + (size_t)l.b_stages * b_stage + 1024;
-    if ((size_t)l.h_b.size() < (size_t)l.Ntile * l.n_tiles) l.h_b.resize((size_t)l.Ntile * l.n_tiles, 0.f);
-    l.h_wimg.assign((size_t)l.n_tiles * l.KB * 2 * l.Ntile * tc::kBlockK, 0.f);
-    for (int nt = 0; nt < l.n_tiles; ++nt)
+    const size_t w_stage = 2 * (size_t)l.Mrows * 128, x_bytes = (size_t)tc::kSiteStages * tc::kSiteStageBytes;
+    const size_t budget = 210 * 1024;        // 227 KB per CTA minus ~15 KB static shared memory and the 1 KB alignment slack
+    l.w_stages = (int)std::min<size_t>(tc::kMaxWStages, std::max<size_t>(2, (budget - x_bytes) / w_stage));
+    l.tc_smem = x_bytes + (size_t)l.w_stages * w_stage + 1024;
+    if ((size_t)l.h_b.size() < (size_t)l.Mrows * l.m_tiles) l.h_b.resize((size_t)l.Mrows * l.m_tiles, 0.f);
+    // image: [weight tile][K block][hi | lo][row = channel within the tile][32 floats, 16-byte chunks XOR-swizzled by row & 7]
+    l.h_wimg.assign((size_t)l.m_tiles * l.KB * 2 * l.Mrows * tc::kBlockK, 0.f);
+    for (int mt = 0; mt < l.m_tiles; ++mt)
         for (int kb = 0; kb < l.KB; ++kb)
-            for (int r = 0; r < l.Ntile; ++r)
+            for (int r = 0; r < l.Mrows; ++r)
                 for (int j = 0; j < 8; ++j)
                     for (int e = 0; e < 4; ++e) {
-                        const int k = kb * tc::kBlockK + 4 * j + e, col = nt * l.Ntile + r;
+                        const int k = kb * tc::kBlockK + 4 * j + e, col = mt * l.Mrows + r;
                         const float w = (k < l.K && col < l.C) ? kernel_hwio[(size_t)k * l.C + col] : 0.f;
                         float hi, lo;
                         split_tf32_host(w, &hi, &lo);
-                        const size_t base = ((size_t)(nt * l.KB + kb) * 2) * l.Ntile * tc::kBlockK;
+                        const size_t base = ((size_t)(mt * l.KB + kb) * 2) * l.Mrows * tc::kBlockK;
                         const size_t off = (size_t)r * tc::kBlockK + (size_t)((j ^ (r & 7)) * 4) + e;
                         l.h_wimg[base + off] = hi;
-                        l.h_wimg[base + (size_t)l.Ntile * tc::kBlockK + off] = lo;
+                        l.h_wimg[base + (size_t)l.Mrows * tc::kBlockK + off] = lo;
                     }
 }
 
@@ -334,10 +338,10 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
     const HostLayer &l = n->L[0];
     IntegrateParams p;
     p.surface = n->surface; p.prev_ts = n->prev_ts; p.delta = n->delta; p.active = n->active;
-    p.front = l.front; p.events = ev; p.offsets = off; p.layer_counts = n->counts; p.err_flag = n->err_flag;
+    p.front = l.front; p.alive = l.nzr; p.events = ev; p.offsets = off; p.layer_counts = n->counts; p.err_flag = n->err_flag;
     p.n_layers = (int)n->L.size();
     p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.leak = n->leak; p.max_events = n->max_events; p.hash_slots = n->hash_slots;
-    const size_t smem = (size_t)n->hash_slots * 8 + (size_t)l.H * l.Ww * 4;
+    const size_t smem = (size_t)n->hash_slots * 8 + (size_t)l.H * l.Ww * 8;
     int rc;
     if ((rc = prof_mark(n, st))) return rc;
     k_integrate<<<n->S, kThreads, smem, st>>>(p);
@@ -345,13 +349,23 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
     return prof_mark(n, st);
 }
 
-static void fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0)
+// Fills one leak-sweep table entry; returns the number of chunks (grid.x slots) the layer takes.
+static int fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0, bool dense_only = false)
 {
     if (l.type == AEC_LAYER_POOL) { o.F = l.Fp; o.A = l.Ap; o.signchg = nullptr; }
     else { o.F = l.F; o.A = l.A; o.signchg = l.signchg; }
     o.fstride = l.fstride;
     o.n4 = (int)(l.fstride / 4); o.chunk0 = chunk0;
     o.C = l.C; o.W = l.W; o.Ww = l.Ww; o.HWw = l.H * l.Ww;
+    o.nzr = (!dense_only && l.C % 4 == 0) ? l.nzr : nullptr;     // a float4 of the sweep must not straddle sites
+    o.c4 = l.C / 4;
+    o.c4_shift = -1;
+    o.wpc = 1;
+    if (!o.nzr) return (o.n4 + kSweepChunk - 1) / kSweepChunk;
+    for (int b = 0; b < 30; ++b)
+        if ((1 << b) == o.c4) o.c4_shift = b;
+    o.wpc = std::max(1, std::min(kSweepMaxWords, kSweepUnitsPerChunk / (32 * o.c4)));
+    return (o.HWw + o.wpc - 1) / o.wpc;
 }
 
 static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
@@ -365,9 +379,9 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
     }
     SweepParams p;
     memset(&p, 0, sizeof p);
-    fill_sweep_layer(n->L[only_layer], p.L[0], 0);
+    const int chunks = fill_sweep_layer(n->L[only_layer], p.L[0], 0);
     p.n_layers = 1; p.delta = n->delta; p.active = n->active;
-    dim3 grid((p.L[0].n4 + kSweepChunk - 1) / kSweepChunk, n->S);
+    dim3 grid(chunks, n->S);
     k_leak_sweep<<<grid, kThreads, 0, st>>>(p);
     return launch_check(n, "k_leak_sweep");
 }
@@ -381,9 +395,12 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     p.srcF = src.F; p.srcA = src.A; p.src_stride = src.fstride; p.alpha = src.alpha;
     p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
     p.wimg = l.wimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
-    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.Ntile = l.Ntile; p.n_tiles = l.n_tiles;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.Mrows = l.Mrows; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
-    p.a_stages = l.a_stages; p.b_stages = l.b_stages; p.n_acc = l.n_acc;
+    p.w_stages = l.w_stages; p.n_acc = l.n_acc;
+    static const int dbg = getenv("AEC_TC_DEBUG") ? atoi(getenv("AEC_TC_DEBUG")) : 0;
+    p.debug = dbg;
+    p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
     tc::k_conv_eval_tc<<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st);
@@ -432,7 +449,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     if (l.type == AEC_LAYER_CONV) {
         if (with_sweep && (rc = run_sweep(n, li, st))) return rc;
         ConvFrontParams p;
-        p.prev_front = pv.front; p.front = l.front; p.signchg = l.signchg; p.active = n->active;
+        p.prev_front = pv.front; p.front = l.front; p.signchg = l.signchg; p.nzr = l.nzr; p.prev_nzr = pv.nzr; p.active = n->active;
         p.sites = n->sites; p.counter = n->counts + li;
         p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
         p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
@@ -444,7 +461,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     }
     if (with_sweep && (rc = run_sweep(n, li, st))) return rc;     // the (Fp, Ap) copy leaks before it is refreshed
     PoolFrontParams p;
-    p.prev_front = pv.front; p.front = l.front; p.flags = l.flags; p.active = n->active;
+    p.prev_front = pv.front; p.front = l.front; p.flags = l.flags; p.nzr = l.nzr; p.prev_nzr = pv.nzr; p.active = n->active;
     p.sites = n->sites; p.counter = n->counts + li;
     p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
     p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
@@ -489,6 +506,7 @@ static int reset_streams(aec_net *n, const uint8_t *mask_dev, cudaStream_t st)
     for (auto &l : n->L) {
         const long long bm = (long long)l.H * l.Ww * 4;
         if ((rc = broadcast(n, l.front, nullptr, bm, bm, mask_dev, st))) return rc;
+        if ((rc = broadcast(n, l.nzr, nullptr, bm, bm, mask_dev, st))) return rc;
         if (l.type == AEC_LAYER_CONV) {
             if ((rc = broadcast(n, l.F, l.initF, l.fstride * 4, l.fstride * 4, mask_dev, st))) return rc;
             if ((rc = broadcast(n, l.A, nullptr, l.fstride * 4, l.fstride * 4, mask_dev, st))) return rc;
@@ -519,6 +537,7 @@ extern "C" int aec_net_finalize(aec_net *n)
     for (auto &l : n->L) {
         const size_t bm = (size_t)l.H * l.Ww;
         if ((rc = dev_alloc(n, &l.front, S * bm, true))) return rc;
+        if ((rc = dev_alloc(n, &l.nzr, S * bm, true))) return rc;
         if (l.type == AEC_LAYER_CONV) {
             if ((rc = dev_alloc(n, &l.F, S * l.fstride, true))) return rc;
             if ((rc = dev_alloc(n, &l.A, S * l.fstride, true))) return rc;
@@ -531,6 +550,7 @@ extern "C" int aec_net_finalize(aec_net *n)
             l.h_w.clear(); l.h_w.shrink_to_fit();
             if (l.tc) {
                 if ((rc = dev_alloc(n, &l.wimg, l.h_wimg.size(), false))) return rc;
+                if ((rc = dev_alloc(n, &l.tc_timing, 16, false))) return rc;
                 CU(cudaMemcpy(l.wimg, l.h_wimg.data(), l.h_wimg.size() * 4, cudaMemcpyHostToDevice));
                 l.h_wimg.clear(); l.h_wimg.shrink_to_fit();
             }
@@ -562,8 +582,7 @@ extern "C" int aec_net_finalize(aec_net *n)
     for (int pass = 0; pass < 2; ++pass) {
         for (auto &l : n->L)
             if (l.type == (pass == 0 ? AEC_LAYER_CONV : AEC_LAYER_POOL)) {
-                fill_sweep_layer(l, n->sweep_all.L[nc], chunk0);
-                chunk0 += (n->sweep_all.L[nc].n4 + kSweepChunk - 1) / kSweepChunk;
+                chunk0 += fill_sweep_layer(l, n->sweep_all.L[nc], chunk0);
                 ++nc;
             }
         if (pass == 0) { n->sweep_nconv = nc; n->sweep_conv_chunks = chunk0; }
@@ -575,7 +594,7 @@ extern "C" int aec_net_finalize(aec_net *n)
 
     // shared-memory opt-ins and persistent grid sizes
     {
-        size_t need = (size_t)n->hash_slots * 8 + (size_t)n->L[0].H * n->L[0].Ww * 4;
+        size_t need = (size_t)n->hash_slots * 8 + (size_t)n->L[0].H * n->L[0].Ww * 8;
         if (need > 200 * 1024) return fail(AEC_EINVAL, "max_events_per_step/surface too large for the surface kernel's shared memory");
         CU(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(need, 48 * 1024)));
         size_t fc = 0, fp = 0;
@@ -595,7 +614,22 @@ extern "C" int aec_net_finalize(aec_net *n)
                 l.tc_blocks = n->num_sms;              // persistent: one warp-specialised CTA per SM (all 512 TMEM columns)
             }
         if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
-        if (tc_max) CU(cudaFuncSetAttribute(tc::k_conv_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
+        if (tc_max) {
+            cudaError_t e = cudaFuncSetAttribute(tc::k_conv_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max);
+            if (e != cudaSuccess) return fail(AEC_ECUDA, "cannot opt in to %zu bytes of dynamic shared memory for the tensor-core conv kernel: %s", tc_max, cudaGetErrorString(e));
+        }
+        if (tc_max) {
+            // the role split (setmaxnreg) must fit the register pool the CTA is launched with, or the
+            // producers' increase would wait forever
+            cudaFuncAttributes fa;
+            CU(cudaFuncGetAttributes(&fa, tc::k_conv_eval_tc));
+            const int pool = fa.numRegs * tc::kTcThreads;
+            const int want = 128 * tc::kRegsEpi + 128 * tc::kRegsCtl + 384 * tc::kRegsProd;
+            if (want > pool || fa.numRegs > tc::kRegsProd || fa.numRegs < tc::kRegsEpi)
+                return fail(AEC_EINVAL, "tensor-core conv kernel was built with %d registers/thread; the role split needs %d of %d", fa.numRegs, want, pool);
+            if (tc_max + fa.sharedSizeBytes > 227 * 1024)
+                return fail(AEC_EINVAL, "tensor-core conv kernel needs %zu + %zu bytes of shared memory", tc_max, (size_t)fa.sharedSizeBytes);
+        }
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));
         n->conv_eval_blocks[0] = std::max(1, b) * n->num_sms;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<32, 4, 4, 16>, kThreads, 0));
@@ -882,9 +916,16 @@ extern "C" int aec_net_count_nonzero_rate_groups(aec_net *n, unsigned long long 
     unsigned long long total = 0;
     for (int i = 0; i < n->sweep_nconv; ++i) total += (unsigned long long)n->sweep_all.L[i].n4 * n->S;
     if (n->sweep_nconv) {
-        SweepParams conv_only = n->sweep_all;
-        conv_only.n_layers = n->sweep_nconv;
-        dim3 grid(n->sweep_conv_chunks, n->S);
+        SweepParams conv_only;
+        memset(&conv_only, 0, sizeof conv_only);
+        int nc = 0, chunk0 = 0;
+        for (auto &l : n->L)
+            if (l.type == AEC_LAYER_CONV) {
+                chunk0 += fill_sweep_layer(l, conv_only.L[nc], chunk0, true);
+                ++nc;
+            }
+        conv_only.n_layers = nc;
+        dim3 grid(chunk0, n->S);
         k_count_nz4<<<grid, kThreads>>>(conv_only, n->accum + 31);
         int rc = launch_check(n, "k_count_nz4");
         if (rc) return rc;
@@ -892,5 +933,21 @@ extern "C" int aec_net_count_nonzero_rate_groups(aec_net *n, unsigned long long 
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(nz_groups, n->accum + 31, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (total_groups) *total_groups = total;
+    return AEC_OK;
+}
+
+extern "C" int aec_net_tc_timing(aec_net *n, int enable, int layer, unsigned long long *out16)
+{
+    NEED_FINAL(n);
+    CU(cudaDeviceSynchronize());
+    if (out16) {
+        if (layer < 1 || layer >= (int)n->L.size() || !n->L[layer].tc_timing)
+            return fail(AEC_EINVAL, "tc_timing: layer %d is not a tensor-core conv layer", layer);
+        CU(cudaMemcpy(out16, n->L[layer].tc_timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        return AEC_OK;
+    }
+    n->tc_timing_on = enable != 0;
+    for (auto &l : n->L)
+        if (l.tc_timing) CU(cudaMemset(l.tc_timing, 0, 16 * sizeof(unsigned long long)));
     return AEC_OK;
 }

@@ -12,6 +12,12 @@
 //   flags_l   uint32 [S][Ho][ceil(Wo/32)]          pool sticky recompute bitmap
 //   front_l   uint32 [S][H_l][ceil(W_l/32)]        output-event ("frontier") bitmap of layer l
 //   signchg_l uint32 [S][H_l][ceil(W_l/32)]        conv sites whose sign flipped in the leak sweep
+//   nzr_l     uint32 [S][H_l][ceil(W_l/32)]        every layer: sites whose leak rate CAN be non-zero.  Layer 0: pixels
+//                                                  with S > 0 (R = [S > 0]).  Conv: a re-evaluated site gets the OR of
+//                                                  its receptive field's input bits (A = W.patch(R) is exactly 0 when
+//                                                  every input rate is 0), other sites keep theirs.  Pool: OR over the
+//                                                  window.  Maintained by the frontier kernels; the leak sweep skips
+//                                                  sites whose bit is 0 (bit 0 => rate exactly 0 => F unchanged)
 //   sites     uint32 [S*max(H_l*W_l)]              gathered work list of the layer being updated:
 //                                                  entry = stream*H_l*W_l + y*W_l + x, streams batched
 //
@@ -177,7 +183,7 @@ __device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int W, int
 //   t_L = max ts; delta = (t_L - t_prev) * leak; S = max(S - delta, 0);
 //   S[p] += 1 - (t_L - ts_j)*leak for the LAST event j on each distinct pixel p (numpy fancy `+=`);
 //   clamp again; frontier = {alive before, dead after} U {event pixels}.
-// Dynamic shared memory: hash_slots * 8 bytes (last-wins hash) + H*Ww*4 (frontier bitmap).
+// Dynamic shared memory: hash_slots * 8 bytes (last-wins hash) + 2 * H*Ww*4 (frontier and alive bitmaps).
 // ---------------------------------------------------------------------------------------------
 struct IntegrateParams {
     double *surface;        // [S][HW]
@@ -185,6 +191,7 @@ struct IntegrateParams {
     double *delta;          // [S]
     uint8_t *active;        // [S]
     uint32_t *front;        // [S][H*Ww]
+    uint32_t *alive;        // [S][H*Ww] pixels with S > 0 after the step (the layer's non-zero-rate bitmap)
     const int32_t *events;  // [total][3] (y,x,ts)
     const int32_t *offsets; // [S+1]
     int *layer_counts;      // [n_layers] work-list counters, zeroed here for the step
@@ -201,6 +208,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
     int *hkey = reinterpret_cast<int *>(smem_raw);
     int *hval = hkey + p.hash_slots;
     uint32_t *bm = reinterpret_cast<uint32_t *>(hval + p.hash_slots);
+    uint32_t *al = bm + p.H * p.Ww;
     __shared__ int s_red[kThreads / 32];
     __shared__ int s_tlast;
 
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
     const int32_t *ev = p.events + (long long)e0 * 3;
 
     for (int i = tid; i < p.hash_slots; i += kThreads) { hkey[i] = -1; hval[i] = -1; }
-    for (int i = tid; i < nbm; i += kThreads) bm[i] = 0u;
+    for (int i = tid; i < nbm; i += kThreads) { bm[i] = 0u; al[i] = 0u; }
 
     // t_L = max(ts)
     int tmax = INT_MIN;
@@ -266,9 +274,9 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
         const bool dead = w <= 0.0;
         const double nv = dead ? 0.0 : w;
         if (nv != v) surf[i] = nv;
-        if (v > 0.0 && dead) {
+        if (v > 0.0) {                 // alive before: died now (output event) or still alive
             const int y = i / p.W, x = i - y * p.W;
-            atomicOr(&bm[y * p.Ww + (x >> 5)], 1u << (x & 31));
+            atomicOr(&(dead ? bm : al)[y * p.Ww + (x >> 5)], 1u << (x & 31));
         }
     }
     __syncthreads();
@@ -287,9 +295,12 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
         if (v <= 0.0) v = 0.0;
         surf[pix] = v;
         atomicOr(&bm[y * p.Ww + (x >> 5)], 1u << (x & 31));
+        if (v > 0.0) atomicOr(&al[y * p.Ww + (x >> 5)], 1u << (x & 31));
+        else atomicAnd(&al[y * p.Ww + (x >> 5)], ~(1u << (x & 31)));
     }
     __syncthreads();
-    for (int i = tid; i < nbm; i += kThreads) front[i] = bm[i];
+    uint32_t *alive = p.alive + (long long)s * nbm;
+    for (int i = tid; i < nbm; i += kThreads) { front[i] = bm[i]; alive[i] = al[i]; }
     if (tid == 0) { p.active[s] = 1; p.delta[s] = delta; p.prev_ts[s] = t_last; }
 }
 
@@ -297,18 +308,26 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
 // K2: leak sweep of all conv layers.   conv2d.py:113-115,126-128
 //   F <- (float)((double)F - (double)A * delta)   [NEP-50 arithmetic of `f32 -= f32 * np.float64`]
 //   sites where sign(F >= 0) flipped in any channel are recorded in signchg.
-// Elements with A == 0 keep F bit-for-bit (x - 0 == x), so F is neither read nor written there.
+// Elements with A == 0 keep F bit-for-bit (x - 0 == x), so F is neither read nor written there, and a
+// site whose non-zero-rate bit (nzr) is clear has A == 0 in every channel, so it is not touched at all:
+// each CTA compacts the live sites of its chunk of bitmap words into shared memory and then streams
+// only their (A, F) vectors, several independent 16-byte loads in flight per thread.
 // The table also holds the pool layers' (Fp, Ap) copies (signchg == nullptr): the same arithmetic on
 // the same bits keeps each copy equal to the conv element it mirrors.
+// Layers whose channel count is not a multiple of 4 (a float4 would straddle sites) take the dense
+// path: chunks of kSweepChunk float4, A read everywhere.
 // Grid: (chunks per stream over all table entries, S).
 // ---------------------------------------------------------------------------------------------
 struct SweepLayer {
     float *F, *A;
     uint32_t *signchg;
+    const uint32_t *nzr;  // [S][H*Ww] sites that can have a non-zero rate (nullptr: dense path)
     long long fstride;   // floats per stream (multiple of 4)
     int n4;              // float4 per stream
     int chunk0;          // first chunk index of this layer
     int C, W, Ww, HWw;   // HWw = H*Ww
+    int wpc;             // sparse path: bitmap words per chunk (<= kSweepMaxWords)
+    int c4, c4_shift;    // C/4 and log2(C/4) (or -1 when C/4 is not a power of two)
 };
 struct SweepParams {
     SweepLayer L[kMaxSweep];
@@ -316,16 +335,34 @@ struct SweepParams {
     const double *delta;
     const uint8_t *active;
 };
-constexpr int kSweepVec = 4;   // float4 per thread per chunk
+constexpr int kSweepVec = 4;   // float4 per thread per iteration
 constexpr int kSweepChunk = kThreads * kSweepVec;
+constexpr int kSweepMaxWords = 64;                     // bitmap words per sparse chunk
+constexpr int kSweepUnitsPerChunk = 8192;              // target float4 per sparse chunk at full density
 
 __device__ __forceinline__ float leak1(float f, float a, double delta)
 {
     return __double2float_rn(__dsub_rn((double)f, __dmul_rn((double)a, delta)));
 }
 
+// Applies the leak to one float4 of F given its rates; returns the flipped-sign lanes (bit e = channel e).
+__device__ __forceinline__ unsigned leak4(float4 *Fp, const float4 av, double delta)
+{
+    const float4 f = *Fp;
+    float4 g;
+    g.x = leak1(f.x, av.x, delta);
+    g.y = leak1(f.y, av.y, delta);
+    g.z = leak1(f.z, av.z, delta);
+    g.w = leak1(f.w, av.w, delta);
+    *Fp = g;
+    return ((f.x >= 0.f) != (g.x >= 0.f) ? 1u : 0u) | ((f.y >= 0.f) != (g.y >= 0.f) ? 2u : 0u) |
+           ((f.z >= 0.f) != (g.z >= 0.f) ? 4u : 0u) | ((f.w >= 0.f) != (g.w >= 0.f) ? 8u : 0u);
+}
+
 __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__ SweepParams p)
 {
+    __shared__ int s_live[kSweepMaxWords * 32];
+    __shared__ int s_scan[9];
     const int s = blockIdx.y;
     if (!p.active[s]) return;
     const double delta = p.delta[s];
@@ -336,10 +373,62 @@ __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__
     for (int i = 1; i < p.n_layers; ++i)
         if (chunk >= p.L[i].chunk0) li = i;
     const SweepLayer &L = p.L[li];
-    const int base = (chunk - L.chunk0) * kSweepChunk;
     const float4 *A4 = reinterpret_cast<const float4 *>(L.A + (long long)s * L.fstride);
     float4 *F4 = reinterpret_cast<float4 *>(L.F + (long long)s * L.fstride);
+    uint32_t *sc = L.signchg ? L.signchg + (long long)s * L.HWw : nullptr;
 
+    if (L.nzr) {
+        // ---- sparse path: compact the live sites of words [w0, w1) ...
+        const int w0 = (chunk - L.chunk0) * L.wpc, w1 = min(L.HWw, w0 + L.wpc);
+        const uint32_t *nz = L.nzr + (long long)s * L.HWw;
+        uint32_t bits = 0u;
+        if ((int)threadIdx.x < w1 - w0) bits = __ldg(nz + w0 + threadIdx.x);
+        int total;
+        int off = block_excl_scan(__popc(bits), s_scan, &total);
+        if (total == 0) return;
+        if (bits) {
+            const int w = w0 + threadIdx.x;
+            const int y = w / L.Ww, xb = (w - y * L.Ww) * 32;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                s_live[off++] = y * L.W + xb + b;
+            }
+        }
+        __syncthreads();
+        // ---- ... and stream their channel vectors: unit u = (live site u / c4, float4 u % c4)
+        const int units = total * L.c4;
+        for (int u0 = threadIdx.x; u0 < units; u0 += kSweepChunk) {
+            float4 a[kSweepVec];
+            int idx[kSweepVec];
+#pragma unroll
+            for (int j = 0; j < kSweepVec; ++j) {
+                const int u = u0 + j * kThreads;
+                idx[j] = -1;
+                a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (u < units) {
+                    const int ls = L.c4_shift >= 0 ? (u >> L.c4_shift) : (u / L.c4);
+                    idx[j] = s_live[ls] * L.c4 + (u - ls * L.c4);
+                    a[j] = A4[idx[j]];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kSweepVec; ++j) {
+                const float4 av = a[j];
+                if (av.x == 0.f && av.y == 0.f && av.z == 0.f && av.w == 0.f) continue;
+                const unsigned flips = leak4(F4 + idx[j], av, delta);
+                if (flips && sc) {
+                    const int site = L.c4_shift >= 0 ? (idx[j] >> L.c4_shift) : (idx[j] / L.c4);
+                    const int y = site / L.W, x = site - y * L.W;
+                    atomicOr(&sc[y * L.Ww + (x >> 5)], 1u << (x & 31));
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- dense path
+    const int base = (chunk - L.chunk0) * kSweepChunk;
     float4 a[kSweepVec];
     int idx[kSweepVec];
 #pragma unroll
@@ -351,17 +440,8 @@ __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__
     for (int j = 0; j < kSweepVec; ++j) {
         const float4 av = a[j];
         if (av.x == 0.f && av.y == 0.f && av.z == 0.f && av.w == 0.f) continue;
-        const float4 f = F4[idx[j]];
-        float4 g;
-        g.x = leak1(f.x, av.x, delta);
-        g.y = leak1(f.y, av.y, delta);
-        g.z = leak1(f.z, av.z, delta);
-        g.w = leak1(f.w, av.w, delta);
-        F4[idx[j]] = g;
-        const unsigned flips = ((f.x >= 0.f) != (g.x >= 0.f) ? 1u : 0u) | ((f.y >= 0.f) != (g.y >= 0.f) ? 2u : 0u) |
-                               ((f.z >= 0.f) != (g.z >= 0.f) ? 4u : 0u) | ((f.w >= 0.f) != (g.w >= 0.f) ? 8u : 0u);
-        if (flips && L.signchg) {
-            uint32_t *sc = L.signchg + (long long)s * L.HWw;
+        const unsigned flips = leak4(F4 + idx[j], av, delta);
+        if (flips && sc) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (flips & (1u << e)) {
@@ -385,6 +465,8 @@ struct ConvFrontParams {
     const uint32_t *prev_front;   // [S][Hin*WwIn]
     uint32_t *front;              // [S][H*Ww]
     uint32_t *signchg;            // [S][H*Ww]  (consumed: cleared)
+    uint32_t *nzr;                // [S][H*Ww]  this layer's non-zero-rate bits
+    const uint32_t *prev_nzr;     // [S][Hin*WwIn] previous layer's
     const uint8_t *active;
     uint32_t *sites;
     int *counter;
@@ -410,31 +492,49 @@ __global__ void __launch_bounds__(kThreads) k_conv_frontier(ConvFrontParams p)
     const uint32_t *pf = p.prev_front + (long long)s * p.Hin * p.WwIn;
     for (int i = tid; i < p.Hin * p.WwIn; i += kThreads) P[i] = pf[i];
     __syncthreads();
-    // horizontal: out x = in x + d, d in [pad_l-kw+1, pad_l]
     const uint32_t lastmask = (p.W & 31) ? ((1u << (p.W & 31)) - 1u) : 0xffffffffu;
-    for (int i = tid; i < p.Hin * p.Ww; i += kThreads) {
-        const int y = i / p.Ww, w = i - y * p.Ww;
-        uint32_t acc = 0u;
-        for (int d = p.pad_l - p.kw + 1; d <= p.pad_l; ++d) acc |= row_shift(P + y * p.WwIn, p.WwIn, w, d);
-        if (w == p.Ww - 1) acc &= lastmask;
-        Hd[i] = acc;
-    }
-    __syncthreads();
+    // horizontal: out x = in x + d, d in [pad_l-kw+1, pad_l]
+    auto hdilate = [&]() {
+        for (int i = tid; i < p.Hin * p.Ww; i += kThreads) {
+            const int y = i / p.Ww, w = i - y * p.Ww;
+            uint32_t acc = 0u;
+            for (int d = p.pad_l - p.kw + 1; d <= p.pad_l; ++d) acc |= row_shift(P + y * p.WwIn, p.WwIn, w, d);
+            if (w == p.Ww - 1) acc &= lastmask;
+            Hd[i] = acc;
+        }
+    };
     // vertical: out y = in y + d, d in [pad_t-kh+1, pad_t]
-    uint32_t *sc = p.signchg + (long long)s * nout;
-    for (int i = tid; i < nout; i += kThreads) {
+    auto vdilate = [&](int i) {
         const int y = i / p.Ww, w = i - y * p.Ww;
         uint32_t acc = 0u;
         for (int d = p.pad_t - p.kh + 1; d <= p.pad_t; ++d) {
             const int yi = y - d;
             if (yi >= 0 && yi < p.Hin) acc |= Hd[yi * p.Ww + w];
         }
+        return acc;
+    };
+    hdilate();
+    __syncthreads();
+    uint32_t *sc = p.signchg + (long long)s * nout;
+    for (int i = tid; i < nout; i += kThreads) {
+        const uint32_t acc = vdilate(i);
         N[i] = acc;
         const uint32_t flips = sc[i];
         if (flips) sc[i] = 0u;
         front[i] = acc | flips;
     }
     __syncthreads();
+    // non-zero-rate bits: re-evaluated sites take the OR of their receptive field's input bits
+    const uint32_t *pn = p.prev_nzr + (long long)s * p.Hin * p.WwIn;
+    for (int i = tid; i < p.Hin * p.WwIn; i += kThreads) P[i] = pn[i];
+    __syncthreads();
+    hdilate();
+    __syncthreads();
+    uint32_t *nz = p.nzr + (long long)s * nout;
+    for (int i = tid; i < nout; i += kThreads) {
+        const uint32_t n = N[i];
+        if (n) nz[i] = (nz[i] & ~n) | (n & vdilate(i));
+    }
     emit_sites(N, p.H, p.W, p.Ww, (uint32_t)s * (uint32_t)(p.H * p.W), p.sites, p.counter, scratch);
 }
 
@@ -448,6 +548,8 @@ struct PoolFrontParams {
     const uint32_t *prev_front;   // [S][Hin*WwIn]
     uint32_t *front;              // [S][H*Ww]
     uint32_t *flags;              // [S][H*Ww]
+    uint32_t *nzr;                // [S][H*Ww]  non-zero-rate bits of the (Fp, Ap) copy
+    const uint32_t *prev_nzr;     // [S][Hin*WwIn] the conv layer's
     const uint8_t *active;
     uint32_t *sites;
     int *counter;
@@ -474,7 +576,8 @@ __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
     __syncthreads();
     uint32_t *fl = p.flags + (long long)s * nout;
     const uint32_t lastmask = (p.W & 31) ? ((1u << (p.W & 31)) - 1u) : 0xffffffffu;
-    for (int i = tid; i < nout; i += kThreads) {
+    // word i of the [H][Ww] bitmap whose bit = OR of the input bitmap P over the window
+    auto window_or = [&](int i) {
         const int oy = i / p.Ww, w = i - oy * p.Ww;
         uint32_t hit = 0u;
         if (p.kh == 2 && p.kw == 2 && p.stride == 2) {
@@ -498,6 +601,10 @@ __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
             }
         }
         if (w == p.Ww - 1) hit &= lastmask;
+        return hit;
+    };
+    for (int i = tid; i < nout; i += kThreads) {
+        const uint32_t hit = window_or(i);
         const uint32_t f = fl[i] & ~hit;      // maxpool.py:118-120
         const uint32_t wset = hit | f;        // maxpool.py:123-126
         fl[i] = f;
@@ -505,6 +612,15 @@ __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
         front[i] = wset;
     }
     __syncthreads();
+    // non-zero-rate bits of the (Fp, Ap) copy: a re-evaluated window copies one of its conv sites
+    const uint32_t *pn = p.prev_nzr + (long long)s * p.Hin * p.WwIn;
+    for (int i = tid; i < p.Hin * p.WwIn; i += kThreads) P[i] = pn[i];
+    __syncthreads();
+    uint32_t *nz = p.nzr + (long long)s * nout;
+    for (int i = tid; i < nout; i += kThreads) {
+        const uint32_t wset = Wb[i];
+        if (wset) nz[i] = (nz[i] & ~wset) | (wset & window_or(i));
+    }
     emit_sites(Wb, p.H, p.W, p.Ww, (uint32_t)s * (uint32_t)(p.H * p.W), p.sites, p.counter, scratch);
 }
 
@@ -831,6 +947,7 @@ __global__ void __launch_bounds__(kThreads) k_layer_view(ViewParams p)
 // K9: measurement helper - number of float4 groups of the leak-rate maps A holding a non-zero
 // (the groups for which the leak sweep must read and write F).  Not on the hot path.
 // ---------------------------------------------------------------------------------------------
+// The caller passes a table whose chunk0 values are dense (kSweepChunk float4 per chunk).
 __global__ void __launch_bounds__(kThreads) k_count_nz4(const __grid_constant__ SweepParams p, unsigned long long *out)
 {
     const int s = blockIdx.y;

@@ -5,29 +5,34 @@
 // at 1-6 % DRAM, ~40 % FMA pipe, ~65 % L1/shared - a dense contraction bound by the SIMT FMA and
 // shared-memory paths, which is the case BASELINE.json's north_star reserves tensor cores for.
 //
-//   rows   M = 128 per m-tile = 64 sites x {value row, rate row}   (conv2d.py:118-123: both maps
-//              use the same gather addresses and the same weights)
-//   K        = kh*kw*Cin ordered (ky,kx,ci), in blocks of 32 (one 128-byte swizzled smem row)
-//   N        = Cout in n-tiles of <= 128 columns
-//   unit     = up to 4 m-tiles x one n-tile: the 4 accumulators (4 x Ntile TMEM columns) share every
-//              weight K block, so weights cross L2 -> shared memory once per 256 sites
+// Orientation (round-1c): the WEIGHTS are the M operand and the gathered sites the N operand,
+//     D[c, n] = sum_k W[k, c] * X[n, k]        M = 128 output channels (one weight tile)
+//                                              N = 256 = 128 sites x {value row, rate row}
+//                                              K = kh*kw*Cin ordered (ky,kx,ci), blocks of 32
+// (conv2d.py:118-123: the value map and the rate map use the same gather addresses and the same
+// weights).  Measured on the previous orientation (sites as M, N = Cout <= 128): the single MMA-issuing
+// thread spends ~115 cycles per tcgen05.mma in uniform-datapath bookkeeping, more than the 16-64
+// cycle tensor floor of such small instructions, so the kernel was issue-bound (AEC_TC_DEBUG
+// ablations, profiles/r1b_summary.md).  With N = 256 every instruction carries 128 cycles of tensor
+// work and the accumulator comes out channel-per-lane, so the epilogue writes 32 consecutive
+// channels of one site per warp store (one 128-byte line) instead of 32 scattered 16-byte pieces.
 //
 // Precision: north_star asks for float32 maps within 1e-4 relative, and the oracle's pool ties must
 // stay exact, so a bare TF32 product (10-bit mantissa) is not enough.  Every operand is split into
 // hi = tf32(x) and lo = x - hi (exact in fp32) and three MMAs are issued per K step:
-//   D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi        ("3xTF32", error ~2^-21 per product)
-// Each accumulator row sees the same instruction sequence whatever its position in a tile, so
+//   D += W_hi.X_lo + W_lo.X_hi + W_hi.X_hi        ("3xTF32", error ~2^-21 per product)
+// Each accumulator column sees the same instruction sequence whatever its position in a tile, so
 // identical patches still produce identical bits (what keeps exact pool ties exact).
 //
 // Warp roles of the persistent CTA (one per SM, 640 threads):
-//   warps 0-3   epilogue: TMEM -> registers -> F (+bias) / A, one accumulator row per thread
+//   warps 0-3   epilogue: TMEM -> registers -> F (+bias) / A, one output channel per thread
 //   warp  4     MMA issuer (one lane): waits operand barriers, issues tcgen05.mma, commits
 //   warp  5     weight loader (one lane): cp.async.bulk of the pre-split, pre-swizzled weight image
-//   warp  6     site decoder: work-list entries -> (stream, y, x) in shared memory, double buffered
-//   warps 8-19  gather producers, 3 groups of 4 warps taking (K block, m-tile) items round-robin:
+//   warp  6     site decoder: work-list entries -> (stream, y, x, output offset), double buffered
+//   warps 8-19  gather producers, 3 groups of 4 warps taking (K block, half) items round-robin:
 //               global -> registers (V = F*slope, R = A*slope) -> hi/lo split -> swizzled smem
-// Pipelines (all mbarrier based): A stages (producers <-> MMA), B stages (loader <-> MMA),
-// accumulator buffers (MMA <-> epilogue; two when 2 x 4 x Ntile <= 512 columns), site-info buffers.
+// Pipelines (all mbarrier based): site stages (producers <-> MMA), weight stages (loader <-> MMA),
+// accumulator buffers (MMA <-> epilogue), site-info buffers (decoder <-> producers/epilogue).
 #pragma once
 #include "aec_kernels.cuh"
 
@@ -39,14 +44,22 @@ constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4, kLoadWarp = 5, kSiteWarp = 6;
 constexpr int kProdWarp0 = 8;
 constexpr int kGroups = 3, kGroupThreads = 128;
-constexpr int kTileSites = 64;                 // sites per m-tile -> 128 accumulator rows
-constexpr int kMT = 4;                         // m-tiles per unit
-constexpr int kUnitSites = kMT * kTileSites;
+constexpr int kItemSites = 64;                 // sites per producer item -> 128 operand rows (value + rate)
+constexpr int kUnitSites = 128;                // sites per unit -> N = 256
+constexpr int kUnitCols = 256;                 // accumulator columns per (unit, weight tile)
 constexpr int kBlockK = 32;                    // fp32 elements per K block (128-byte rows)
-constexpr int kATileBytes = 128 * 128;         // one A tile (hi or lo): 128 rows x 128 bytes
-constexpr int kAStageBytes = 2 * kATileBytes;
-constexpr int kMaxNtile = 128;
-constexpr int kMaxStages = 8;
+constexpr int kItemTileBytes = 128 * 128;      // one item's hi (or lo) rows: 128 rows x 128 bytes
+constexpr int kSiteTileBytes = 2 * kItemTileBytes;   // hi (or lo) tile of a site stage: 256 rows
+constexpr int kSiteStageBytes = 2 * kSiteTileBytes;  // hi + lo
+constexpr int kSiteStages = 2;
+constexpr int kMaxWStages = 4;
+constexpr int kMaxMtu = 2;                     // weight tiles per unit (2 x 256 accumulator columns)
+constexpr int kSiteRing = 4;                   // site-info buffers: producers may run this many units ahead of the epilogue
+constexpr int kKtabBlocks = 64;                // K blocks covered by the shared-memory gather table (larger K: computed on the fly)
+// Registers per thread after the role split (setmaxnreg): the producers double buffer a whole item
+// (2 x 8 float4) in registers so that their global loads are in flight while the previous item is
+// converted and while the shared-memory stage is still owned by the tensor core.
+constexpr int kRegsEpi = 80, kRegsCtl = 64, kRegsProd = 112;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,6 +142,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// True in exactly one lane of a converged warp.  The MMA / loader warps run their loops converged on
+// warp-uniform values and guard only the issuing instructions with this, so ptxas keeps descriptors
+// in uniform registers and emits back-to-back UTCHMMA (a `lane == 0` branch around the whole loop
+// costs ~10 bookkeeping instructions and a per-instruction ELECT/BRA loop for every MMA).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // hi = x rounded to tf32 (10 explicit mantissa bits, low 13 bits zero), lo = x - hi exactly.
@@ -146,17 +169,34 @@ struct TcParams {
     long long src_stride;       // floats per stream
     float alpha;                // previous layer's activation slope
     int Cin, Hin, Win;
-    const float *wimg;          // [n_tiles][KB][2][Ntile][32] pre-split (hi, lo), pre-swizzled weight image
-    const float *bias;          // [Ntile * n_tiles]
+    const float *wimg;          // [m_tiles][KB][2][Mrows][32] pre-split (hi, lo), pre-swizzled weight image
+    const float *bias;          // [Mrows * m_tiles]
     float *F, *A;
     long long fstride;
     int C, H, W;                // output map
     int K, KB;                  // contraction length, number of 32-wide K blocks
-    int Ntile, n_tiles;         // columns per n-tile (multiple of 16, <= 128), n-tiles
+    int Mrows, m_tiles;         // output channels per weight tile (multiple of 8, <= 128), weight tiles
+    int mtu;                    // weight tiles per unit (1 or 2): the unit's sites are gathered once for all of them
     int kh, kw, pad_t, pad_l;
-    int a_stages, b_stages;     // shared-memory pipeline depths
-    int n_acc;                  // accumulator buffers in TMEM (1 or 2)
+    int w_stages;               // weight pipeline depth
+    int n_acc;                  // accumulator buffers in TMEM (2 when mtu == 1, else 1)
+    unsigned long long *timing; // null, or 16 cycle counters accumulated over CTAs (aec_net_tc_timing): see TcTimingSlot
+    int debug;                  // AEC_TC_DEBUG experiment bits (results invalid when non-zero): 1 no gather loads, 2 no operand stores, 4 no MMA, 8 no epilogue stores, 16 no weight copies
 };
+
+// Cycle accounting per warp role (measurement only; active when TcParams::timing != nullptr).
+enum TcTimingSlot { kTMmaTotal = 0, kTMmaWaitAcc, kTMmaWaitX, kTMmaWaitW, kTProdTotal, kTProdWaitSite, kTProdWaitStage, kTEpiTotal,
+                    kTEpiWaitAcc, kTEpiWaitSite, kTLoadTotal, kTLoadWaitW, kTCtas, kTUnits };
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, long long &acc)
+{
+    if (on) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 
 // byte offset of 16-byte chunk j of row r inside a 128-byte-swizzled tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)); }
@@ -172,23 +212,38 @@ __device__ __forceinline__ void store_split(unsigned char *a_hi, unsigned char *
     *reinterpret_cast<float4 *>(a_lo + off) = l;
 }
 
-// One (K block, m-tile) item of the A operand: 64 sites x 8 chunks of 4 channels gathered by one
-// producer group; thread t owns chunk t&7 of sites (t>>3) + 16u, u = 0..3.  Value rows are 0..63,
-// rate rows 64..127 of the tile.
-__device__ __forceinline__ void gather_item(const TcParams &p, int kb, int m, const int *ss, const int *syx, unsigned char *a_hi,
-                                            unsigned char *a_lo, int t)
+// Gather-table entry of (K block, 16-byte chunk j): where the 4 channels k = 32*kb + 4*j .. +3 of a
+// site's patch live relative to the site's own pixel, and whether the tap can fall outside the map.
+struct KEntry {
+    int rel;      // float offset from the site's pixel (y*Win + x)*Cin
+    int tap;      // (dy + 128) | (dx + 128) << 8 | valid << 16
+};
+__device__ __forceinline__ KEntry make_kentry(const TcParams &p, int kb, int j)
 {
-    const int j = t & 7, tq = t >> 3;
     const int k = kb * kBlockK + 4 * j;
     const int tap = k / p.Cin, c = k - tap * p.Cin;
     const int ky = tap / p.kw, kx = tap - ky * p.kw;
     const int dy = ky - p.pad_t, dx = kx - p.pad_l;
-    const bool kvalid = k < p.K;
-    const int rel = (dy * p.Win + dx) * p.Cin + c;
-    float4 f[4], a[4];
+    KEntry e;
+    e.rel = (dy * p.Win + dx) * p.Cin + c;
+    e.tap = (dy + 128) | ((dx + 128) << 8) | ((k < p.K ? 1 : 0) << 16);
+    return e;
+}
+
+// One (K block, half) item of the site operand: 64 sites x 8 chunks of 4 channels gathered by one
+// producer group; thread t owns chunk t&7 of sites (t>>3) + 16u, u = 0..3.  Value rows are 0..63,
+// rate rows 64..127 of the item's 128 rows.  `ss`/`syx` point at the item's first site.
+// item_load issues the 8 global loads; item_store converts (V = F*slope, R = A*slope), splits and
+// writes the swizzled operand rows - the caller overlaps the two across consecutive items.
+__device__ __forceinline__ void item_load(const TcParams &p, const KEntry e, const int *ss, const int *syx, int t, float4 (&f)[4],
+                                          float4 (&a)[4])
+{
+    const int tq = t >> 3;
+    const int dy = (e.tap & 0xff) - 128, dx = ((e.tap >> 8) & 0xff) - 128;
+    const bool kvalid = (e.tap >> 16) != 0 && !(p.debug & 1);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int i = m * kTileSites + tq + 16 * u;
+        const int i = tq + 16 * u;
         const int s = ss[i];
         const int yx = syx[i];
         const int y = yx >> 16, x = yx & 0xffff;
@@ -196,11 +251,18 @@ __device__ __forceinline__ void gather_item(const TcParams &p, int kb, int m, co
         f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         a[u] = f[u];
         if (ok) {
-            const long long off = (long long)s * p.src_stride + ((y * p.Win + x) * p.Cin + rel);
+            const long long off = (long long)s * p.src_stride + ((y * p.Win + x) * p.Cin + e.rel);
             f[u] = __ldg(reinterpret_cast<const float4 *>(p.srcF + off));
             a[u] = __ldg(reinterpret_cast<const float4 *>(p.srcA + off));
         }
     }
+}
+
+__device__ __forceinline__ void item_store(const TcParams &p, unsigned char *x_hi, unsigned char *x_lo, int t, const float4 (&f)[4],
+                                           const float4 (&a)[4])
+{
+    if (p.debug & 2) return;
+    const int j = t & 7, tq = t >> 3;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int r = tq + 16 * u;
@@ -210,52 +272,58 @@ __device__ __forceinline__ void gather_item(const TcParams &p, int kb, int m, co
         sl = slope_of(f[u].y, p.alpha); v.y = __fmul_rn(f[u].y, sl); w.y = __fmul_rn(a[u].y, sl);
         sl = slope_of(f[u].z, p.alpha); v.z = __fmul_rn(f[u].z, sl); w.z = __fmul_rn(a[u].z, sl);
         sl = slope_of(f[u].w, p.alpha); v.w = __fmul_rn(f[u].w, sl); w.w = __fmul_rn(a[u].w, sl);
-        store_split(a_hi, a_lo, sw128_off(r, j), v);
-        store_split(a_hi, a_lo, sw128_off(kTileSites + r, j), w);
+        store_split(x_hi, x_lo, sw128_off(r, j), v);
+        store_split(x_hi, x_lo, sw128_off(kItemSites + r, j), w);
     }
 }
 
-// Dynamic shared memory: [pad to 1024][a_stages x {A_hi 16K, A_lo 16K}][b_stages x {B_hi, B_lo: Ntile*128 each}]
+// Dynamic shared memory: [pad to 1024][w_stages x {W_hi, W_lo: Mrows*128 bytes each}][2 x {X_hi 32K, X_lo 32K}].
+// The weight stages come first: the A descriptor always spans 128 rows, so with Mrows < 128 it reads
+// past the tile into whatever follows (the next stage / the site stages); those rows only feed
+// accumulator lanes >= Mrows, which the epilogue never reads.
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ __align__(8) uint64_t bar_a_full[kMaxStages], bar_a_empty[kMaxStages], bar_b_full[kMaxStages], bar_b_empty[kMaxStages];
-    __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[2], bar_si_free[2];
+    __shared__ __align__(8) uint64_t bar_x_full[kSiteStages][2], bar_x_empty[kSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
+    __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[kSiteRing], bar_si_free[kSiteRing];
     __shared__ uint32_t s_tmem;
-    __shared__ int s_str[2][kUnitSites], s_yx[2][kUnitSites];
+    __shared__ int s_str[kSiteRing][kUnitSites], s_yx[kSiteRing][kUnitSites];
+    __shared__ __align__(16) long long s_dst[kSiteRing][kUnitSites];   // byte offset of the site's channel 0 in F (and in A)
+    __shared__ KEntry s_ktab[kKtabBlocks * 8];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_sites = *p.counter;
+    const int n_sites = __shfl_sync(0xffffffffu, *p.counter, 0);      // warp-uniform for the compiler's sake
     if (blockIdx.x == 0 && tid == 0 && n_sites > 0) atomicAdd(p.accum, (unsigned long long)n_sites);
-    const int m_tiles = (n_sites + kTileSites - 1) / kTileSites;
-    // m-tiles per unit: 4 when there is enough work to keep every CTA busy, fewer for short lists
-    int mte = kMT;
-    while (mte > 1 && (long long)((m_tiles + mte - 1) / mte) * p.n_tiles < 4LL * gridDim.x) mte >>= 1;
-    const int m_groups = (m_tiles + mte - 1) / mte;
-    const int total_units = m_groups * p.n_tiles;
+    const int n_blocks = (n_sites + kUnitSites - 1) / kUnitSites;
+    const int n_mgroups = (p.m_tiles + p.mtu - 1) / p.mtu;
+    const int total_units = n_blocks * n_mgroups;
     if ((int)blockIdx.x >= total_units) return;       // uniform per CTA: nothing allocated yet
 
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *smem_b = smem + (size_t)p.a_stages * kAStageBytes;
-    const uint32_t b_bytes = (uint32_t)p.Ntile * 128u;            // one B tile (hi or lo)
+    unsigned char *smem_w = reinterpret_cast<unsigned char *>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t w_tile = (uint32_t)p.Mrows * 128u;             // one weight tile (hi or lo)
+    unsigned char *smem_x = smem_w + (size_t)p.w_stages * 2 * w_tile;
 
     if (tid == 0) {
-        for (int i = 0; i < p.a_stages; ++i) {
-            mbar_init(smem_u32(&bar_a_full[i]), kGroupThreads);
-            mbar_init(smem_u32(&bar_a_empty[i]), 1);
+        for (int i = 0; i < kSiteStages; ++i) {
+            mbar_init(smem_u32(&bar_x_full[i][0]), kGroupThreads);
+            mbar_init(smem_u32(&bar_x_full[i][1]), kGroupThreads);
+            mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
-        for (int i = 0; i < p.b_stages; ++i) {
-            mbar_init(smem_u32(&bar_b_full[i]), 1);
-            mbar_init(smem_u32(&bar_b_empty[i]), 1);
+        for (int i = 0; i < p.w_stages; ++i) {
+            mbar_init(smem_u32(&bar_w_full[i]), 1);
+            mbar_init(smem_u32(&bar_w_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bar_acc_full[i]), 1);
             mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps * 32);
+        }
+        for (int i = 0; i < kSiteRing; ++i) {
             mbar_init(smem_u32(&bar_si_full[i]), 1);
             mbar_init(smem_u32(&bar_si_free[i]), kEpiWarps * 32);
         }
         fence_barrier_init();
     }
+    for (int i = tid; i < min(p.KB, kKtabBlocks) * 8; i += kTcThreads) s_ktab[i] = make_kentry(p, i >> 3, i & 7);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -263,58 +331,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = s_tmem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
     const int HW = p.H * p.W;
+    const bool timing = p.timing != nullptr;
+    // register re-balancing between the roles happens at the top of each role branch (setmaxnreg works on
+    // warpgroups: warps 0-3 epilogue, 4-7 control roles, 8-19 producers)
     const int n_units_cta = (total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp < kEpiWarps) {
         // ===================== epilogue =====================
-        const int row = warp * 32 + lane;                   // TMEM lane == accumulator row
-        const bool is_rate = row >= kTileSites;
-        const int sr = row & (kTileSites - 1);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+        // TMEM lane == row of the weight tile == output channel; columns == (site, map) rows.
+        const int row = warp * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float *const dst_map = is_rate ? p.A : p.F;
-        const bool vec_ok = (p.C & 3) == 0;
+        const bool warp_live = warp * 32 < p.Mrows;          // warps whose 32 lanes hold no channel only arrive
+        long long tw_acc = 0, tw_si = 0;
+        const long long t_begin = timing ? clock64() : 0;
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
-            const int mg = unit / p.n_tiles, nt = unit - mg * p.n_tiles;
-            const int mt_count = min(mte, m_tiles - mg * mte);
-            const int buf = ul & 1, ab = ul % p.n_acc;
-            mbar_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul >> 1) & 1u);
-            mbar_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u);
+            const int mg = unit % n_mgroups;
+            const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+            const int buf = ul % kSiteRing, ab = ul % p.n_acc;
+            timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul / kSiteRing) & 1u, timing, tw_si);
+            timed_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u, timing, tw_acc);
             tc_fence_after();
-            for (int m = 0; m < mt_count; ++m) {
-                const int s = s_str[buf][m * kTileSites + sr];
-                const int yx = s_yx[buf][m * kTileSites + sr];
-                float *dst = nullptr;
-                if (s >= 0) dst = dst_map + (long long)s * p.fstride + (long long)((yx >> 16) * p.W + (yx & 0xffff)) * p.C;
-                const uint32_t col0 = (uint32_t)(ab * kMT * p.Ntile + m * p.Ntile);
-                for (int cc = 0; cc < p.Ntile; cc += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(lane_addr + col0 + (uint32_t)cc, r);
-                    tmem_ld_wait();
-                    if (dst) {
-                        const int n = nt * p.Ntile + cc;
-                        float o[16];
+            if (warp_live) {
+                for (int mt = 0; mt < mt_count; ++mt) {
+                    const int c = (mg * p.mtu + mt) * p.Mrows + row;
+                    const bool c_ok = row < p.Mrows && c < p.C && !(p.debug & 8);
+                    const long long a_minus_f = (const char *)p.A - (const char *)p.F;
+                    const float bias = c_ok ? __ldg(p.bias + c) : 0.f;
+                    const uint32_t taddr = lane_addr + (uint32_t)((ab * p.mtu + mt) * kUnitCols);
+                    // 16 columns (= 16 sites of one map) per step, TMEM loads double buffered against the stores
+                    uint32_t ra[16], rb[16];
+                    auto store16 = [&](const uint32_t(&r)[16], int cc) {
+                        const bool is_rate = (cc & 64) != 0;                 // columns 64..127 of each 128-column half
+                        const int i0 = (cc >> 7) * kItemSites + (cc & 63);   // first site of these 16 columns
+                        const longlong2 *po = reinterpret_cast<const longlong2 *>(&s_dst[buf][i0]);
+                        if (po[0].x < 0 || !c_ok) return;                    // valid sites are a prefix of the unit
+                        char *const base = (char *)p.F + (long long)c * 4 + (is_rate ? a_minus_f : 0LL);
+                        const float add = is_rate ? 0.f : bias;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]);
-                        if (!is_rate) {
-#pragma unroll
-                            for (int e = 0; e < 16; e += 4) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + n + e));
-                                o[e] = __fadd_rn(o[e], bv.x); o[e + 1] = __fadd_rn(o[e + 1], bv.y);
-                                o[e + 2] = __fadd_rn(o[e + 2], bv.z); o[e + 3] = __fadd_rn(o[e + 3], bv.w);
-                            }
+                        for (int e = 0; e < 8; ++e) {
+                            const longlong2 o = po[e];
+                            const float v0 = __uint_as_float(r[2 * e]), v1 = __uint_as_float(r[2 * e + 1]);
+                            if (o.x >= 0) *reinterpret_cast<float *>(base + o.x) = is_rate ? v0 : __fadd_rn(v0, add);
+                            if (o.y >= 0) *reinterpret_cast<float *>(base + o.y) = is_rate ? v1 : __fadd_rn(v1, add);
                         }
-                        if (vec_ok && n + 16 <= p.C) {
-#pragma unroll
-                            for (int e = 0; e < 16; e += 4)
-                                *reinterpret_cast<float4 *>(dst + n + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                if (n + e < p.C) dst[n + e] = o[e];
-                        }
+                    };
+                    tmem_ld16(taddr, ra);
+#pragma unroll 1
+                    for (int cc = 0; cc < kUnitCols; cc += 32) {
+                        tmem_ld_wait();
+                        tmem_ld16(taddr + (uint32_t)(cc + 16), rb);
+                        store16(ra, cc);
+                        tmem_ld_wait();
+                        if (cc + 32 < kUnitCols) tmem_ld16(taddr + (uint32_t)(cc + 32), ra);
+                        store16(rb, cc + 16);
                     }
                 }
             }
@@ -322,115 +395,192 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             mbar_arrive(smem_u32(&bar_acc_empty[ab]));
             mbar_arrive(smem_u32(&bar_si_free[buf]));
         }
-    } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(p.Ntile);
-            uint32_t q = 0, qb = 0;
-            for (int ul = 0; ul < n_units_cta; ++ul) {
-                const int unit = blockIdx.x + ul * gridDim.x;
-                const int mg = unit / p.n_tiles;
-                const int mt_count = min(mte, m_tiles - mg * mte);
-                const int ab = ul % p.n_acc;
-                const uint32_t ua = (uint32_t)(ul / p.n_acc);
-                if (ua > 0) mbar_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u);    // epilogue drained this buffer
-                tc_fence_after();
-                for (int kb = 0; kb < p.KB; ++kb, ++qb) {
-                    const int sb = (int)(qb % (uint32_t)p.b_stages);
-                    mbar_wait(smem_u32(&bar_b_full[sb]), (qb / (uint32_t)p.b_stages) & 1u);
-                    const uint32_t b_hi = smem_u32(smem_b + (size_t)sb * 2 * b_bytes), b_lo = b_hi + b_bytes;
-                    for (int m = 0; m < mt_count; ++m, ++q) {
-                        const int sa = (int)(q % (uint32_t)p.a_stages);
-                        mbar_wait(smem_u32(&bar_a_full[sa]), (q / (uint32_t)p.a_stages) & 1u);
-                        tc_fence_after();
-                        const uint32_t a_hi = smem_u32(smem + (size_t)sa * kAStageBytes), a_lo = a_hi + kATileBytes;
-                        const uint32_t d = tmem_base + (uint32_t)(ab * kMT * p.Ntile + m * p.Ntile);
-#pragma unroll
-                        for (int ks = 0; ks < kBlockK / 8; ++ks) {
-                            const uint32_t ko = (uint32_t)ks * 32u;       // 8 tf32 = 32 bytes along K inside the swizzled row
-                            const uint64_t dah = make_desc_sw128(a_hi + ko), dal = make_desc_sw128(a_lo + ko);
-                            const uint64_t dbh = make_desc_sw128(b_hi + ko), dbl = make_desc_sw128(b_lo + ko);
-                            mma_tf32(d, dal, dbh, idesc, (kb | ks) != 0 ? 1u : 0u);
-                            mma_tf32(d, dah, dbl, idesc, 1u);
-                            mma_tf32(d, dah, dbh, idesc, 1u);
-                        }
-                        mma_commit(smem_u32(&bar_a_empty[sa]));
-                    }
-                    mma_commit(smem_u32(&bar_b_empty[sb]));
-                }
-                mma_commit(smem_u32(&bar_acc_full[ab]));
-            }
+        if (timing && tid == 0) {
+            atomicAdd(p.timing + kTEpiTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTEpiWaitAcc, (unsigned long long)tw_acc);
+            atomicAdd(p.timing + kTEpiWaitSite, (unsigned long long)tw_si);
+            atomicAdd(p.timing + kTCtas, 1ULL);
+            atomicAdd(p.timing + kTUnits, (unsigned long long)n_units_cta);
         }
-    } else if (warp == kLoadWarp) {
+    } else if (warp < kProdWarp0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+      if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        // The whole warp runs the loop converged (waits included); one elected lane issues.
+        const uint32_t idesc = make_idesc_tf32(kUnitCols);
+        const uint32_t x_base = smem_u32(smem_x), w_base = smem_u32(smem_w);
+        uint32_t qx = 0, qw = 0;
+        long long tw_acc = 0, tw_x = 0, tw_w = 0;
+        const long long t_begin = timing ? clock64() : 0;
+        for (int ul = 0; ul < n_units_cta; ++ul) {
+            const int unit = blockIdx.x + ul * gridDim.x;
+            const int mg = unit % n_mgroups;
+            const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+            const int ab = ul % p.n_acc;
+            const uint32_t ua = (uint32_t)(ul / p.n_acc);
+            if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
+            tc_fence_after();
+            for (int kb = 0; kb < p.KB; ++kb, ++qx) {
+                const uint32_t sx = qx % (uint32_t)kSiteStages;
+                const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
+                timed_wait(smem_u32(&bar_x_full[sx][0]), px, timing, tw_x);
+                timed_wait(smem_u32(&bar_x_full[sx][1]), px, timing, tw_x);
+                tc_fence_after();
+                const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes, x_lo = x_hi + (uint32_t)kSiteTileBytes;
+                for (int mt = 0; mt < mt_count; ++mt, ++qw) {
+                    const uint32_t sw = qw % (uint32_t)p.w_stages;
+                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                    const uint32_t w_hi = w_base + sw * 2u * w_tile, w_lo = w_hi + w_tile;
+                    const uint32_t d = tmem_base + (uint32_t)((ab * p.mtu + mt) * kUnitCols);
+                    if (elect_one()) {
+                        if (!(p.debug & 4)) {
+#pragma unroll
+                            for (int ks = 0; ks < kBlockK / 8; ++ks) {
+                                const uint32_t ko = (uint32_t)ks * 32u;       // 8 tf32 = 32 bytes along K inside the swizzled row
+                                const uint64_t dwh = make_desc_sw128(w_hi + ko), dwl = make_desc_sw128(w_lo + ko);
+                                const uint64_t dxh = make_desc_sw128(x_hi + ko), dxl = make_desc_sw128(x_lo + ko);
+                                mma_tf32(d, dwh, dxl, idesc, (kb | ks) != 0 ? 1u : 0u);
+                                mma_tf32(d, dwl, dxh, idesc, 1u);
+                                mma_tf32(d, dwh, dxh, idesc, 1u);
+                            }
+                        }
+                        mma_commit(smem_u32(&bar_w_empty[sw]));
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) mma_commit(smem_u32(&bar_x_empty[sx]));
+                __syncwarp();
+            }
+            if (elect_one()) mma_commit(smem_u32(&bar_acc_full[ab]));
+            __syncwarp();
+        }
+        if (timing && lane == 0) {
+            atomicAdd(p.timing + kTMmaTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTMmaWaitAcc, (unsigned long long)tw_acc);
+            atomicAdd(p.timing + kTMmaWaitX, (unsigned long long)tw_x);
+            atomicAdd(p.timing + kTMmaWaitW, (unsigned long long)tw_w);
+        }
+      } else if (warp == kLoadWarp) {
         // ===================== weight loader =====================
         if (lane == 0) {
-            uint32_t qb = 0;
+            uint32_t qw = 0;
+            long long tw_w = 0;
+            const long long t_begin = timing ? clock64() : 0;
+            const size_t tile_floats = (size_t)2 * p.Mrows * kBlockK;        // hi + lo of one (weight tile, K block)
             for (int ul = 0; ul < n_units_cta; ++ul) {
                 const int unit = blockIdx.x + ul * gridDim.x;
-                const int nt = unit % p.n_tiles;
-                const float *wtile = p.wimg + (size_t)nt * p.KB * 2 * p.Ntile * kBlockK;
-                for (int kb = 0; kb < p.KB; ++kb, ++qb) {
-                    const int sb = (int)(qb % (uint32_t)p.b_stages);
-                    const uint32_t use = qb / (uint32_t)p.b_stages;
-                    if (use > 0) mbar_wait(smem_u32(&bar_b_empty[sb]), (use - 1) & 1u);
-                    mbar_expect_tx(smem_u32(&bar_b_full[sb]), 2u * b_bytes);
-                    bulk_g2s(smem_u32(smem_b + (size_t)sb * 2 * b_bytes), wtile + (size_t)kb * 2 * p.Ntile * kBlockK, 2u * b_bytes,
-                             smem_u32(&bar_b_full[sb]));
+                const int mg = unit % n_mgroups;
+                const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    for (int mt = 0; mt < mt_count; ++mt, ++qw) {
+                        const int sw = (int)(qw % (uint32_t)p.w_stages);
+                        const uint32_t use = qw / (uint32_t)p.w_stages;
+                        if (use > 0) timed_wait(smem_u32(&bar_w_empty[sw]), (use - 1) & 1u, timing, tw_w);
+                        const float *src = p.wimg + ((size_t)(mg * p.mtu + mt) * p.KB + kb) * tile_floats;
+                        if (p.debug & 16) { mbar_arrive(smem_u32(&bar_w_full[sw])); continue; }
+                        mbar_expect_tx(smem_u32(&bar_w_full[sw]), 2u * w_tile);
+                        bulk_g2s(smem_u32(smem_w + (size_t)sw * 2 * w_tile), src, 2u * w_tile, smem_u32(&bar_w_full[sw]));
+                    }
                 }
             }
+            if (timing) {
+                atomicAdd(p.timing + kTLoadTotal, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(p.timing + kTLoadWaitW, (unsigned long long)tw_w);
+            }
         }
-    } else if (warp == kSiteWarp) {
+      } else if (warp == kSiteWarp) {
         // ===================== site decoder =====================
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
-            const int mg = unit / p.n_tiles;
-            const int mt_count = min(mte, m_tiles - mg * mte);
-            const int buf = ul & 1;
-            const uint32_t us = (uint32_t)(ul >> 1);
+            const int blk = unit / n_mgroups;
+            const int buf = ul % kSiteRing;
+            const uint32_t us = (uint32_t)(ul / kSiteRing);
             if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
             for (int i = lane; i < kUnitSites; i += 32) {
-                const long long gi = (long long)mg * mte * kTileSites + i;
+                const long long gi = (long long)blk * kUnitSites + i;
                 int s = -1, yx = 0;
-                if (i < mt_count * kTileSites && gi < n_sites) {
+                long long dst = -1;
+                if (gi < n_sites) {
                     const uint32_t e = p.sites[gi];
                     s = (int)(e / (uint32_t)HW);
                     const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
                     const int y = site / p.W;
                     yx = (y << 16) | (site - y * p.W);
+                    dst = ((long long)s * p.fstride + (long long)site * p.C) * 4;
                 }
                 s_str[buf][i] = s;
                 s_yx[buf][i] = yx;
+                s_dst[buf][i] = dst;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_si_full[buf]));
         }
-    } else if (warp >= kProdWarp0) {
+      }
+    } else {
         // ===================== gather producers =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+        // Items are numbered q = 2 * (unit-local K block counter) + half over the CTA's whole life; group g
+        // takes q = g, g + 3, ...  The loads of the group's next item are issued before the current item is
+        // converted and stored, so global latency overlaps both the conversion and the wait for the stage.
         const int pt = tid - kProdWarp0 * 32;
         const int g = pt / kGroupThreads, t = pt - g * kGroupThreads;
-        uint32_t q = 0;
-        for (int ul = 0; ul < n_units_cta; ++ul) {
-            const int unit = blockIdx.x + ul * gridDim.x;
-            const int mg = unit / p.n_tiles;
-            const int mt_count = min(mte, m_tiles - mg * mte);
-            const int buf = ul & 1;
-            bool waited = false;
-            for (int kb = 0; kb < p.KB; ++kb) {
-                for (int m = 0; m < mt_count; ++m, ++q) {
-                    if ((int)(q % (uint32_t)kGroups) != g) continue;
-                    if (!waited) {
-                        mbar_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul >> 1) & 1u);
-                        waited = true;
-                    }
-                    const int sa = (int)(q % (uint32_t)p.a_stages);
-                    const uint32_t use = q / (uint32_t)p.a_stages;
-                    if (use > 0) mbar_wait(smem_u32(&bar_a_empty[sa]), (use - 1) & 1u);   // MMAs that read this stage are done
-                    unsigned char *a_hi = smem + (size_t)sa * kAStageBytes;
-                    gather_item(p, kb, m, s_str[buf], s_yx[buf], a_hi, a_hi + kATileBytes, t);
-                    fence_proxy_async();      // generic-proxy writes of A -> visible to the tensor core (async proxy)
-                    mbar_arrive(smem_u32(&bar_a_full[sa]));
-                }
+        long long tw_si = 0, tw_x = 0;
+        const long long t_begin = timing ? clock64() : 0;
+        const uint32_t q_end = (uint32_t)n_units_cta * (uint32_t)p.KB * 2u;
+        struct Pos { int ul, kb, h; uint32_t q; };
+        auto advance = [&](Pos &c) {
+            c.q += kGroups;
+            c.h += kGroups;
+            while (c.h >= 2) {
+                c.h -= 2;
+                if (++c.kb == p.KB) { c.kb = 0; ++c.ul; }
             }
+        };
+        int ready_ul = -1;                 // units whose site info this thread has already waited for
+        auto load = [&](const Pos &c, float4 (&f)[4], float4 (&a)[4]) {
+            const int buf = c.ul % kSiteRing;
+            if (c.ul > ready_ul) {
+                timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(c.ul / kSiteRing) & 1u, timing, tw_si);
+                ready_ul = c.ul;
+            }
+            const KEntry e = c.kb < kKtabBlocks ? s_ktab[c.kb * 8 + (t & 7)] : make_kentry(p, c.kb, t & 7);
+            item_load(p, e, s_str[buf] + c.h * kItemSites, s_yx[buf] + c.h * kItemSites, t, f, a);
+        };
+        auto store = [&](const Pos &c, const float4 (&f)[4], const float4 (&a)[4]) {
+            const uint32_t qx = c.q >> 1;
+            const uint32_t sx = qx % (uint32_t)kSiteStages, use = qx / (uint32_t)kSiteStages;
+            if (use > 0) timed_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
+            unsigned char *x_hi = smem_x + (size_t)sx * kSiteStageBytes + (size_t)c.h * kItemTileBytes;
+            item_store(p, x_hi, x_hi + kSiteTileBytes, t, f, a);
+            fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
+            mbar_arrive(smem_u32(&bar_x_full[sx][c.h]));
+        };
+        Pos cur;
+        cur.q = (uint32_t)g; cur.ul = 0; cur.kb = 0; cur.h = g;
+        while (cur.h >= 2) {
+            cur.h -= 2;
+            if (++cur.kb == p.KB) { cur.kb = 0; ++cur.ul; }
+        }
+        float4 fa[4], aa[4], fb[4], ab4[4];
+        if (cur.q < q_end) {
+            load(cur, fa, aa);
+            while (true) {
+                Pos nxt = cur;
+                advance(nxt);
+                if (nxt.q < q_end) load(nxt, fb, ab4);
+                store(cur, fa, aa);
+                if (nxt.q >= q_end) break;
+                cur = nxt;
+                advance(cur);
+                if (cur.q < q_end) load(cur, fa, aa);
+                store(nxt, fb, ab4);
+                if (cur.q >= q_end) break;
+            }
+        }
+        if (timing && pt == 0) {
+            atomicAdd(p.timing + kTProdTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTProdWaitSite, (unsigned long long)tw_si);
+            atomicAdd(p.timing + kTProdWaitStage, (unsigned long long)tw_x);
         }
     }
 

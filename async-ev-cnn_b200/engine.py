@@ -255,6 +255,22 @@ class EventNetCuda:
         k = max(1, int(steps.value))
         return {names[i]: ms[i] / k for i in range(min(n, len(names)))}, int(steps.value)
 
+    TC_TIMING_SLOTS = ("mma_total", "mma_wait_acc", "mma_wait_sites", "mma_wait_weights", "prod_total", "prod_wait_siteinfo",
+                       "prod_wait_stage", "epi_total", "epi_wait_acc", "epi_wait_siteinfo", "load_total", "load_wait", "ctas", "units")
+
+    def tc_timing(self, enable=True):
+        N.check(self._lib.aec_net_tc_timing(self._h, 1 if enable else 0, 0, None))
+
+    def read_tc_timing(self):
+        """-> {layer name: {slot: cycles summed over CTAs and launches}} for the tensor-core conv layers."""
+        out = {}
+        for i, nm in enumerate(self.names):
+            buf = np.zeros(16, np.uint64)
+            rc = self._lib.aec_net_tc_timing(self._h, 0, i, _ptr(buf))
+            if rc == 0:
+                out[nm] = {k: int(buf[j]) for j, k in enumerate(self.TC_TIMING_SLOTS)}
+        return out
+
     def nonzero_rate_fraction(self):
         nz, tot = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
         N.check(self._lib.aec_net_count_nonzero_rate_groups(self._h, ctypes.byref(nz), ctypes.byref(tot)))

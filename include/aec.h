@@ -204,6 +204,15 @@ int aec_net_read_profile(aec_net *net, double *ms_per_slot, int n_slots, unsigne
  */
 int aec_net_count_nonzero_rate_groups(aec_net *net, unsigned long long *nz_groups, unsigned long long *total_groups);
 
+/*
+ * Measurement helper for the tensor-core conv kernel: with out16 == NULL, enables (enable != 0) or
+ * disables per-role cycle accounting and clears the counters; with out16 != NULL copies the 16
+ * counters of conv layer `layer` (summed over CTAs and launches since enabling: MMA-warp total /
+ * waiting for accumulator, sites, weights; producer total / waiting for site info, stage; epilogue
+ * total / waiting for accumulator, site info; loader total / waiting; CTAs; units).  Synchronises.
+ */
+int aec_net_tc_timing(aec_net *net, int enable, int layer, unsigned long long *out16);
+
 /* Number of kernels this library has launched since creation of `net` (for bench `gpu_launches`). */
 unsigned long long aec_net_launch_count(const aec_net *net);
 
