@@ -114,6 +114,18 @@ static int dev_alloc(aec_net *n, T **out, size_t count, bool per_stream)
     return AEC_OK;
 }
 
+// Float maps gathered by the tensor-core conv kernel (F, A, Fp, Ap) get kMapGuardFloats zero floats in
+// front of them: an out-of-map tap reads that line instead of branching (aec_tc.cuh: item_load).
+static const int kMapGuardFloats = 32;
+static int dev_alloc_map(aec_net *n, float **out, size_t count)
+{
+    float *base = nullptr;
+    int rc = dev_alloc(n, &base, count + kMapGuardFloats, true);
+    if (rc) return rc;
+    *out = base + kMapGuardFloats;
+    return AEC_OK;
+}
+
 extern "C" const char *aec_last_error(void) { return g_err.c_str(); }
 extern "C" int aec_version(void) { return 1000; }
 
@@ -175,7 +187,7 @@ static void split_tf32_host(float x, float *hi, float *lo)
 static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_hwio)
 {
     const char *force = getenv("AEC_CONV_PATH");
-    l.tc = prev_is_map && (l.Cin % 4 == 0) && !(force && strcmp(force, "simt") == 0);
+    l.tc = prev_is_map && (l.Cin % 4 == 0) && l.kh * l.kw <= 32 && !(force && strcmp(force, "simt") == 0);
     if (!l.tc) return;
     const int c8 = (l.C + 7) / 8 * 8;
     l.m_tiles = (c8 + 127) / 128;
@@ -392,12 +404,14 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     const Src src = make_src(n, li - 1);
     tc::TcParams p;
     p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
-    p.srcF = src.F; p.srcA = src.A; p.src_stride = src.fstride; p.alpha = src.alpha;
+    p.srcF = src.F; p.a_minus_f = (const char *)src.A - (const char *)src.F; p.zero_f = (const char *)src.F - kMapGuardFloats * 4;
+    p.src_stride = src.fstride; p.alpha = src.alpha;
     p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
     p.wimg = l.wimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
-    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.Mrows = l.Mrows; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
+
     static const int dbg = getenv("AEC_TC_DEBUG") ? atoi(getenv("AEC_TC_DEBUG")) : 0;
     p.debug = dbg;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
@@ -539,8 +553,8 @@ extern "C" int aec_net_finalize(aec_net *n)
         if ((rc = dev_alloc(n, &l.front, S * bm, true))) return rc;
         if ((rc = dev_alloc(n, &l.nzr, S * bm, true))) return rc;
         if (l.type == AEC_LAYER_CONV) {
-            if ((rc = dev_alloc(n, &l.F, S * l.fstride, true))) return rc;
-            if ((rc = dev_alloc(n, &l.A, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc_map(n, &l.F, S * l.fstride))) return rc;
+            if ((rc = dev_alloc_map(n, &l.A, S * l.fstride))) return rc;
             if ((rc = dev_alloc(n, &l.signchg, S * bm, true))) return rc;
             if ((rc = dev_alloc(n, &l.initF, (size_t)l.fstride, false))) return rc;
             if ((rc = dev_alloc(n, &l.wgt, l.h_w.size(), false))) return rc;
@@ -558,8 +572,8 @@ extern "C" int aec_net_finalize(aec_net *n)
             if ((rc = dev_alloc(n, &l.idx, S * l.fstride, true))) return rc;
             if ((rc = dev_alloc(n, &l.flags, S * bm, true))) return rc;
             if ((rc = dev_alloc(n, &l.initIdx, (size_t)l.fstride, false))) return rc;
-            if ((rc = dev_alloc(n, &l.Fp, S * l.fstride, true))) return rc;
-            if ((rc = dev_alloc(n, &l.Ap, S * l.fstride, true))) return rc;
+            if ((rc = dev_alloc_map(n, &l.Fp, S * l.fstride))) return rc;
+            if ((rc = dev_alloc_map(n, &l.Ap, S * l.fstride))) return rc;
             if ((rc = dev_alloc(n, &l.initFp, (size_t)l.fstride, false))) return rc;
         }
         if (l.type != AEC_LAYER_INTEGRATION) maxHW = std::max(maxHW, (size_t)l.H * l.W);

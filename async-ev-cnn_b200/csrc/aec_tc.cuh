@@ -26,7 +26,8 @@
 //
 // Warp roles of the persistent CTA (one per SM, 640 threads):
 //   warps 0-3   epilogue: TMEM -> registers -> F (+bias) / A, one output channel per thread
-//   warp  4     MMA issuer (one lane): waits operand barriers, issues tcgen05.mma, commits
+//   warp  4     MMA issuer: a converged warp, one elected lane issues tcgen05.mma and the commits
+//   warp  7     gatekeeper: does every mbarrier wait on the MMA warp's behalf (named-barrier hand-off)
 //   warp  5     weight loader (one lane): cp.async.bulk of the pre-split, pre-swizzled weight image
 //   warp  6     site decoder: work-list entries -> (stream, y, x, output offset), double buffered
 //   warps 8-19  gather producers, 3 groups of 4 warps taking (K block, half) items round-robin:
@@ -41,10 +42,11 @@ namespace tc {
 
 constexpr int kTcThreads = 640;
 constexpr int kEpiWarps = 4;
-constexpr int kMmaWarp = 4, kLoadWarp = 5, kSiteWarp = 6;
+constexpr int kMmaWarp = 4, kLoadWarp = 5, kSiteWarp = 6, kGateWarp = 7;
 constexpr int kProdWarp0 = 8;
-constexpr int kGroups = 3, kGroupThreads = 128;
-constexpr int kItemSites = 64;                 // sites per producer item -> 128 operand rows (value + rate)
+constexpr int kGroups = 3, kGroupThreads = 128; // gather warps 8-19: 3 groups of 4 warps
+constexpr int kPairs = 4;                      // (site, chunk) pairs per producer thread and item
+constexpr int kItemSites = 64;                 // sites per half stage -> 128 operand rows (value rows, then rate rows)
 constexpr int kUnitSites = 128;                // sites per unit -> N = 256
 constexpr int kUnitCols = 256;                 // accumulator columns per (unit, weight tile)
 constexpr int kBlockK = 32;                    // fp32 elements per K block (128-byte rows)
@@ -165,7 +167,9 @@ struct TcParams {
     const uint32_t *sites;
     const int *counter;
     unsigned long long *accum;
-    const float *srcF, *srcA;   // previous layer's channel-last (F, A) pair (conv state or pool copy)
+    const float *srcF;          // previous layer's channel-last F map (conv state or pool copy); A = F + a_minus_f bytes
+    long long a_minus_f;        // byte distance from the source F map to the source A map (same layout)
+    const char *zero_f;         // the 128 zero bytes in front of the source F map (in front of A after adding a_minus_f)
     long long src_stride;       // floats per stream
     float alpha;                // previous layer's activation slope
     int Cin, Hin, Win;
@@ -175,6 +179,7 @@ struct TcParams {
     long long fstride;
     int C, H, W;                // output map
     int K, KB;                  // contraction length, number of 32-wide K blocks
+    int ks_last;                // 8-wide MMA steps of the last K block: ceil((K - 32*(KB-1)) / 8), the rest is padding
     int Mrows, m_tiles;         // output channels per weight tile (multiple of 8, <= 128), weight tiles
     int mtu;                    // weight tiles per unit (1 or 2): the unit's sites are gathered once for all of them
     int kh, kw, pad_t, pad_l;
@@ -186,7 +191,7 @@ struct TcParams {
 
 // Cycle accounting per warp role (measurement only; active when TcParams::timing != nullptr).
 enum TcTimingSlot { kTMmaTotal = 0, kTMmaWaitAcc, kTMmaWaitX, kTMmaWaitW, kTProdTotal, kTProdWaitSite, kTProdWaitStage, kTEpiTotal,
-                    kTEpiWaitAcc, kTEpiWaitSite, kTLoadTotal, kTLoadWaitW, kTCtas, kTUnits };
+                    kTEpiWaitAcc, kTEpiWaitSite, kTLoadTotal, kTLoadWaitW, kTCtas, kTUnits, kTGateWaitX };
 __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, long long &acc)
 {
     if (on) {
@@ -201,79 +206,95 @@ __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool o
 // byte offset of 16-byte chunk j of row r inside a 128-byte-swizzled tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void store_split(unsigned char *a_hi, unsigned char *a_lo, uint32_t off, const float4 &v)
-{
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x);
-    split_tf32(v.y, h.y, l.y);
-    split_tf32(v.z, h.z, l.z);
-    split_tf32(v.w, h.w, l.w);
-    *reinterpret_cast<float4 *>(a_hi + off) = h;
-    *reinterpret_cast<float4 *>(a_lo + off) = l;
-}
-
 // Gather-table entry of (K block, 16-byte chunk j): where the 4 channels k = 32*kb + 4*j .. +3 of a
-// site's patch live relative to the site's own pixel, and whether the tap can fall outside the map.
+// site's patch live relative to the site's own pixel, and which tap they belong to.
 struct KEntry {
-    int rel;      // float offset from the site's pixel (y*Win + x)*Cin
-    int tap;      // (dy + 128) | (dx + 128) << 8 | valid << 16
+    int relb;     // byte offset from the site's pixel (y*Win + x)*Cin*4
+    int tap;      // tap index ky*kw + kx (< 32), or -1 for the K padding beyond kh*kw*Cin
 };
 __device__ __forceinline__ KEntry make_kentry(const TcParams &p, int kb, int j)
 {
     const int k = kb * kBlockK + 4 * j;
     const int tap = k / p.Cin, c = k - tap * p.Cin;
     const int ky = tap / p.kw, kx = tap - ky * p.kw;
-    const int dy = ky - p.pad_t, dx = kx - p.pad_l;
     KEntry e;
-    e.rel = (dy * p.Win + dx) * p.Cin + c;
-    e.tap = (dy + 128) | ((dx + 128) << 8) | ((k < p.K ? 1 : 0) << 16);
+    e.relb = (((ky - p.pad_t) * p.Win + (kx - p.pad_l)) * p.Cin + c) * 4;
+    e.tap = k < p.K ? tap : -1;
     return e;
 }
 
+// What the site decoder leaves for the producers, per site of a unit: the address of the site's own input
+// pixel (channel 0) in the source F map, and one bit per tap (kh*kw <= 32) telling whether the tap is
+// inside the map; 0 for the padding sites of a partial unit, so that they gather nothing.
+struct __align__(16) SiteSrc {
+    const char *ptr;
+    uint32_t taps;
+    uint32_t pad;
+};
+
 // One (K block, half) item of the site operand: 64 sites x 8 chunks of 4 channels gathered by one
 // producer group; thread t owns chunk t&7 of sites (t>>3) + 16u, u = 0..3.  Value rows are 0..63,
-// rate rows 64..127 of the item's 128 rows.  `ss`/`syx` point at the item's first site.
-// item_load issues the 8 global loads; item_store converts (V = F*slope, R = A*slope), splits and
-// writes the swizzled operand rows - the caller overlaps the two across consecutive items.
-__device__ __forceinline__ void item_load(const TcParams &p, const KEntry e, const int *ss, const int *syx, int t, float4 (&f)[4],
-                                          float4 (&a)[4])
+// rate rows 64..127 of the item's 128 rows.  `ss` points at the item's first site.
+// item_load issues the 8 global loads, branch-free: a tap outside the map (or K padding, or a padding
+// site) reads the 128 zero bytes every map is allocated with in front of it - the same negative offset
+// is a zero line for F and for A - so no register is cleared and no branch is taken.  item_store
+// converts (V = F*slope, R = A*slope), splits and writes the swizzled operand rows; the caller
+// overlaps the two across consecutive items.
+__device__ __forceinline__ void item_load(const TcParams &p, const KEntry e, const SiteSrc *ss, int t, float4 (&f)[kPairs], float4 (&a)[kPairs])
 {
     const int tq = t >> 3;
-    const int dy = (e.tap & 0xff) - 128, dx = ((e.tap >> 8) & 0xff) - 128;
-    const bool kvalid = (e.tap >> 16) != 0 && !(p.debug & 1);
+    const uint32_t tapbit = e.tap >= 0 && !(p.debug & 1) ? 1u << e.tap : 0u;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int i = tq + 16 * u;
-        const int s = ss[i];
-        const int yx = syx[i];
-        const int y = yx >> 16, x = yx & 0xffff;
-        const bool ok = kvalid && s >= 0 && (unsigned)(y + dy) < (unsigned)p.Hin && (unsigned)(x + dx) < (unsigned)p.Win;
-        f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        a[u] = f[u];
-        if (ok) {
-            const long long off = (long long)s * p.src_stride + ((y * p.Win + x) * p.Cin + e.rel);
-            f[u] = __ldg(reinterpret_cast<const float4 *>(p.srcF + off));
-            a[u] = __ldg(reinterpret_cast<const float4 *>(p.srcA + off));
-        }
+    for (int u = 0; u < kPairs; ++u) {
+        const SiteSrc q = ss[tq + 16 * u];
+        const char *pf = (q.taps & tapbit) ? q.ptr + e.relb : p.zero_f;
+        f[u] = __ldg(reinterpret_cast<const float4 *>(pf));
+        a[u] = __ldg(reinterpret_cast<const float4 *>(pf + p.a_minus_f));
     }
 }
 
-__device__ __forceinline__ void item_store(const TcParams &p, unsigned char *x_hi, unsigned char *x_lo, int t, const float4 (&f)[4],
-                                           const float4 (&a)[4])
+// 16-byte store to a shared-memory address (the generic `*ptr = v` form compiles to ST.E with a 64-bit
+// address, and makes the following proxy fence a full MEMBAR that also waits for the prefetched loads).
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 &v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// hi = x with the low 13 mantissa bits cleared (a tf32 value), lo = x - hi (exact); two lanes at a time
+// on the packed fp32 pipe.  Truncation instead of rounding keeps |lo| < 2^-10 |x|, which the tf32
+// product of lo still resolves to 2^-21 |x|.
+__device__ __forceinline__ void split2(float x0, float x1, float &h0, float &h1, float &l0, float &l1)
+{
+    h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
+    h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+    const float2 l = __ffma2_rn(make_float2(h0, h1), make_float2(-1.f, -1.f), make_float2(x0, x1));
+    l0 = l.x;
+    l1 = l.y;
+}
+
+__device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uint32_t x_lo, int t, const float4 (&f)[kPairs],
+                                           const float4 (&a)[kPairs])
 {
     if (p.debug & 2) return;
     const int j = t & 7, tq = t >> 3;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kPairs; ++u) {
         const int r = tq + 16 * u;
-        float4 v, w;
-        float sl;
-        sl = slope_of(f[u].x, p.alpha); v.x = __fmul_rn(f[u].x, sl); w.x = __fmul_rn(a[u].x, sl);
-        sl = slope_of(f[u].y, p.alpha); v.y = __fmul_rn(f[u].y, sl); w.y = __fmul_rn(a[u].y, sl);
-        sl = slope_of(f[u].z, p.alpha); v.z = __fmul_rn(f[u].z, sl); w.z = __fmul_rn(a[u].z, sl);
-        sl = slope_of(f[u].w, p.alpha); v.w = __fmul_rn(f[u].w, sl); w.w = __fmul_rn(a[u].w, sl);
-        store_split(x_hi, x_lo, sw128_off(r, j), v);
-        store_split(x_hi, x_lo, sw128_off(kItemSites + r, j), w);
+        const float2 s01 = make_float2(slope_of(f[u].x, p.alpha), slope_of(f[u].y, p.alpha));
+        const float2 s23 = make_float2(slope_of(f[u].z, p.alpha), slope_of(f[u].w, p.alpha));
+        const float2 v01 = __fmul2_rn(make_float2(f[u].x, f[u].y), s01), v23 = __fmul2_rn(make_float2(f[u].z, f[u].w), s23);
+        const float2 w01 = __fmul2_rn(make_float2(a[u].x, a[u].y), s01), w23 = __fmul2_rn(make_float2(a[u].z, a[u].w), s23);
+        float4 h, l;
+        split2(v01.x, v01.y, h.x, h.y, l.x, l.y);
+        split2(v23.x, v23.y, h.z, h.w, l.z, l.w);
+        const uint32_t ov = sw128_off(r, j);
+        sts128(x_hi + ov, h);
+        sts128(x_lo + ov, l);
+        split2(w01.x, w01.y, h.x, h.y, l.x, l.y);
+        split2(w23.x, w23.y, h.z, h.w, l.z, l.w);
+        const uint32_t ow = ov + (uint32_t)(kItemSites / 8) * 1024u;      // rate row = value row + 64 (same swizzle phase)
+        sts128(x_hi + ow, h);
+        sts128(x_lo + ow, l);
     }
 }
 
@@ -287,7 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     __shared__ __align__(8) uint64_t bar_x_full[kSiteStages][2], bar_x_empty[kSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[kSiteRing], bar_si_free[kSiteRing];
     __shared__ uint32_t s_tmem;
-    __shared__ int s_str[kSiteRing][kUnitSites], s_yx[kSiteRing][kUnitSites];
+    __shared__ __align__(16) SiteSrc s_src[kSiteRing][kUnitSites];
     __shared__ __align__(16) long long s_dst[kSiteRing][kUnitSites];   // byte offset of the site's channel 0 in F (and in A)
     __shared__ KEntry s_ktab[kKtabBlocks * 8];
 
@@ -334,8 +355,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
     const int HW = p.H * p.W;
     const bool timing = p.timing != nullptr;
-    // register re-balancing between the roles happens at the top of each role branch (setmaxnreg works on
-    // warpgroups: warps 0-3 epilogue, 4-7 control roles, 8-19 producers)
     const int n_units_cta = (total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp < kEpiWarps) {
@@ -406,32 +425,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
       if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
-        // The whole warp runs the loop converged (waits included); one elected lane issues.
+        // The whole warp runs the loop converged; one elected lane issues.  It executes NO mbarrier wait:
+        // measured (tools/bench_umma.cu), every mbarrier.try_wait in the issuing warp costs ~170 cycles
+        // that the tensor pipe idles (the wait queues behind the in-flight MMAs), so all operand waits
+        // live in the gatekeeper warp, which releases each pass through a named barrier (ids 1..4).
         const uint32_t idesc = make_idesc_tf32(kUnitCols);
         const uint32_t x_base = smem_u32(smem_x), w_base = smem_u32(smem_w);
         uint32_t qx = 0, qw = 0;
-        long long tw_acc = 0, tw_x = 0, tw_w = 0;
+        long long tw_gate = 0;
         const long long t_begin = timing ? clock64() : 0;
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
             const int mg = unit % n_mgroups;
             const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
             const int ab = ul % p.n_acc;
-            const uint32_t ua = (uint32_t)(ul / p.n_acc);
-            if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
-            tc_fence_after();
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
                 const uint32_t sx = qx % (uint32_t)kSiteStages;
-                const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
-                timed_wait(smem_u32(&bar_x_full[sx][0]), px, timing, tw_x);
-                timed_wait(smem_u32(&bar_x_full[sx][1]), px, timing, tw_x);
-                tc_fence_after();
                 const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes, x_lo = x_hi + (uint32_t)kSiteTileBytes;
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
-                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
                     const uint32_t w_hi = w_base + sw * 2u * w_tile, w_lo = w_hi + w_tile;
                     const uint32_t d = tmem_base + (uint32_t)((ab * p.mtu + mt) * kUnitCols);
+                    const int ks_n = kb == p.KB - 1 ? p.ks_last : kBlockK / 8;
+                    const long long t0 = timing ? clock64() : 0;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1u + (qw & 3u)) : "memory");     // operands (and accumulator) ready
+                    if (timing) tw_gate += clock64() - t0;
+                    tc_fence_after();
                     if (elect_one()) {
                         if (!(p.debug & 4)) {
 #pragma unroll
@@ -439,26 +458,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                                 const uint32_t ko = (uint32_t)ks * 32u;       // 8 tf32 = 32 bytes along K inside the swizzled row
                                 const uint64_t dwh = make_desc_sw128(w_hi + ko), dwl = make_desc_sw128(w_lo + ko);
                                 const uint64_t dxh = make_desc_sw128(x_hi + ko), dxl = make_desc_sw128(x_lo + ko);
+                                if (ks >= ks_n) break;
                                 mma_tf32(d, dwh, dxl, idesc, (kb | ks) != 0 ? 1u : 0u);
                                 mma_tf32(d, dwl, dxh, idesc, 1u);
                                 mma_tf32(d, dwh, dxh, idesc, 1u);
                             }
                         }
                         mma_commit(smem_u32(&bar_w_empty[sw]));
+                        if (mt == mt_count - 1) mma_commit(smem_u32(&bar_x_empty[sx]));
+                        if (mt == mt_count - 1 && kb == p.KB - 1) mma_commit(smem_u32(&bar_acc_full[ab]));
                     }
                     __syncwarp();
                 }
-                if (elect_one()) mma_commit(smem_u32(&bar_x_empty[sx]));
-                __syncwarp();
             }
-            if (elect_one()) mma_commit(smem_u32(&bar_acc_full[ab]));
-            __syncwarp();
         }
         if (timing && lane == 0) {
             atomicAdd(p.timing + kTMmaTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTMmaWaitX, (unsigned long long)tw_gate);
+        }
+      } else if (warp == kGateWarp) {
+        // ===================== gatekeeper =====================
+        // Waits for everything pass qw needs - accumulator drained (first pass of a unit), both halves of the
+        // site stage, the weight stage - then arrives on named barrier 1 + (qw & 3).  An id is reused every
+        // 4 passes; the site stage of pass qw can only be full once the MMA warp has committed the passes
+        // two K blocks back, i.e. has passed barrier qw - 4, so arrivals never pile up on one id.
+        uint32_t qx = 0, qw = 0;
+        long long tw_acc = 0, tw_x = 0, tw_w = 0;
+        for (int ul = 0; ul < n_units_cta; ++ul) {
+            const int unit = blockIdx.x + ul * gridDim.x;
+            const int mg = unit % n_mgroups;
+            const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+            const int ab = ul % p.n_acc;
+            const uint32_t ua = (uint32_t)(ul / p.n_acc);
+            if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
+            for (int kb = 0; kb < p.KB; ++kb, ++qx) {
+                const uint32_t sx = qx % (uint32_t)kSiteStages;
+                const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
+                timed_wait(smem_u32(&bar_x_full[sx][0]), px, timing, tw_x);
+                timed_wait(smem_u32(&bar_x_full[sx][1]), px, timing, tw_x);
+                for (int mt = 0; mt < mt_count; ++mt, ++qw) {
+                    const uint32_t sw = qw % (uint32_t)p.w_stages;
+                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                    asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qw & 3u)) : "memory");
+                }
+            }
+        }
+        if (timing && lane == 0) {
             atomicAdd(p.timing + kTMmaWaitAcc, (unsigned long long)tw_acc);
-            atomicAdd(p.timing + kTMmaWaitX, (unsigned long long)tw_x);
             atomicAdd(p.timing + kTMmaWaitW, (unsigned long long)tw_w);
+            atomicAdd(p.timing + kTGateWaitX, (unsigned long long)tw_x);
         }
       } else if (warp == kLoadWarp) {
         // ===================== weight loader =====================
@@ -498,18 +546,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
             for (int i = lane; i < kUnitSites; i += 32) {
                 const long long gi = (long long)blk * kUnitSites + i;
-                int s = -1, yx = 0;
+                SiteSrc q;
+                q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
                 long long dst = -1;
                 if (gi < n_sites) {
                     const uint32_t e = p.sites[gi];
-                    s = (int)(e / (uint32_t)HW);
+                    const int s = (int)(e / (uint32_t)HW);
                     const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
-                    const int y = site / p.W;
-                    yx = (y << 16) | (site - y * p.W);
+                    const int y = site / p.W, x = site - y * p.W;
+                    q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
+                    for (int ky = 0, tap = 0; ky < p.kh; ++ky)
+                        for (int kx = 0; kx < p.kw; ++kx, ++tap)
+                            if ((unsigned)(y + ky - p.pad_t) < (unsigned)p.Hin && (unsigned)(x + kx - p.pad_l) < (unsigned)p.Win) q.taps |= 1u << tap;
                     dst = ((long long)s * p.fstride + (long long)site * p.C) * 4;
                 }
-                s_str[buf][i] = s;
-                s_yx[buf][i] = yx;
+                s_src[buf][i] = q;
                 s_dst[buf][i] = dst;
             }
             __syncwarp();
@@ -518,10 +569,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
       }
     } else {
         // ===================== gather producers =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
         // Items are numbered q = 2 * (unit-local K block counter) + half over the CTA's whole life; group g
         // takes q = g, g + 3, ...  The loads of the group's next item are issued before the current item is
-        // converted and stored, so global latency overlaps both the conversion and the wait for the stage.
+        // converted and stored, so global latency overlaps the conversion and the wait for the stage.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
         const int pt = tid - kProdWarp0 * 32;
         const int g = pt / kGroupThreads, t = pt - g * kGroupThreads;
         long long tw_si = 0, tw_x = 0;
@@ -531,37 +582,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         auto advance = [&](Pos &c) {
             c.q += kGroups;
             c.h += kGroups;
-            while (c.h >= 2) {
-                c.h -= 2;
-                if (++c.kb == p.KB) { c.kb = 0; ++c.ul; }
-            }
+            c.kb += c.h >> 1;
+            c.h &= 1;
+            while (c.kb >= p.KB) { c.kb -= p.KB; ++c.ul; }
         };
         int ready_ul = -1;                 // units whose site info this thread has already waited for
-        auto load = [&](const Pos &c, float4 (&f)[4], float4 (&a)[4]) {
+        auto load = [&](const Pos &c, float4 (&f)[kPairs], float4 (&a)[kPairs]) {
             const int buf = c.ul % kSiteRing;
             if (c.ul > ready_ul) {
                 timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(c.ul / kSiteRing) & 1u, timing, tw_si);
                 ready_ul = c.ul;
             }
             const KEntry e = c.kb < kKtabBlocks ? s_ktab[c.kb * 8 + (t & 7)] : make_kentry(p, c.kb, t & 7);
-            item_load(p, e, s_str[buf] + c.h * kItemSites, s_yx[buf] + c.h * kItemSites, t, f, a);
+            item_load(p, e, s_src[buf] + c.h * kItemSites, t, f, a);
         };
-        auto store = [&](const Pos &c, const float4 (&f)[4], const float4 (&a)[4]) {
+        const uint32_t x_base = smem_u32(smem_x);
+        auto store = [&](const Pos &c, const float4 (&f)[kPairs], const float4 (&a)[kPairs]) {
             const uint32_t qx = c.q >> 1;
             const uint32_t sx = qx % (uint32_t)kSiteStages, use = qx / (uint32_t)kSiteStages;
             if (use > 0) timed_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
-            unsigned char *x_hi = smem_x + (size_t)sx * kSiteStageBytes + (size_t)c.h * kItemTileBytes;
-            item_store(p, x_hi, x_hi + kSiteTileBytes, t, f, a);
+            const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes + (uint32_t)c.h * (uint32_t)kItemTileBytes;
+            item_store(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
             fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
             mbar_arrive(smem_u32(&bar_x_full[sx][c.h]));
         };
         Pos cur;
-        cur.q = (uint32_t)g; cur.ul = 0; cur.kb = 0; cur.h = g;
-        while (cur.h >= 2) {
-            cur.h -= 2;
-            if (++cur.kb == p.KB) { cur.kb = 0; ++cur.ul; }
-        }
-        float4 fa[4], aa[4], fb[4], ab4[4];
+        cur.q = (uint32_t)g; cur.ul = 0; cur.kb = g >> 1; cur.h = g & 1;
+        while (cur.kb >= p.KB) { cur.kb -= p.KB; ++cur.ul; }
+        float4 fa[kPairs], aa[kPairs], fb[kPairs], ab4[kPairs];
         if (cur.q < q_end) {
             load(cur, fa, aa);
             while (true) {
