@@ -965,3 +965,31 @@ extern "C" int aec_net_tc_timing(aec_net *n, int enable, int layer, unsigned lon
         if (l.tc_timing) CU(cudaMemset(l.tc_timing, 0, 16 * sizeof(unsigned long long)));
     return AEC_OK;
 }
+
+extern "C" int aec_net_sweep_stats(aec_net *n, unsigned long long *out6)
+{
+    NEED_FINAL(n);
+    if (!out6) return fail(AEC_EINVAL, "sweep_stats: out is NULL");
+    unsigned long long nz = 0, tot = 0;
+    int rc = aec_net_count_nonzero_rate_groups(n, &nz, &tot);
+    if (rc) return rc;
+    out6[0] = nz;
+    out6[1] = tot;
+    unsigned long long live_conv = 0, all_conv = 0, live_pool = 0, all_pool = 0;
+    for (auto &l : n->L) {
+        if (l.type == AEC_LAYER_INTEGRATION) continue;
+        const long long words = (long long)n->S * l.H * l.Ww;
+        CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
+        k_count_bits<<<std::min<long long>((words + kThreads - 1) / kThreads, (long long)n->num_sms * 8), kThreads>>>(l.nzr, words, n->accum + 31);
+        if ((rc = launch_check(n, "k_count_bits"))) return rc;
+        unsigned long long bits = 0;
+        CU(cudaMemcpy(&bits, n->accum + 31, sizeof bits, cudaMemcpyDeviceToHost));
+        const unsigned long long all = (unsigned long long)n->S * l.H * l.W * l.C;
+        if (l.C % 4) bits = (unsigned long long)n->S * l.H * l.W;      // dense path of the sweep: every site is read
+        if (l.type == AEC_LAYER_CONV) { live_conv += bits * l.C; all_conv += all; }
+        else { live_pool += bits * l.C; all_pool += all; }
+    }
+    CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
+    out6[2] = live_conv; out6[3] = all_conv; out6[4] = live_pool; out6[5] = all_pool;
+    return AEC_OK;
+}

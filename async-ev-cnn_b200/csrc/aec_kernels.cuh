@@ -972,6 +972,16 @@ __global__ void __launch_bounds__(kThreads) k_count_nz4(const __grid_constant__ 
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
 }
 
+// K9b: measurement helper - number of set bits of a [S][words] bitmap (live sites of a layer).
+__global__ void __launch_bounds__(kThreads) k_count_bits(const uint32_t *bm, long long words, unsigned long long *out)
+{
+    int cnt = 0;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < words; i += (long long)gridDim.x * kThreads) cnt += __popc(bm[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
 // ---------------------------------------------------------------------------------------------
 // utility kernels: reset / init plumbing
 // ---------------------------------------------------------------------------------------------

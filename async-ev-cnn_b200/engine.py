@@ -255,6 +255,23 @@ class EventNetCuda:
         k = max(1, int(steps.value))
         return {names[i]: ms[i] / k for i in range(min(n, len(names)))}, int(steps.value)
 
+    def sweep_stats(self):
+        """Leak-sweep work of the current state: dict with the fraction of conv-map 16-byte groups whose rate is
+        non-zero, and the conv / pool-copy elements at live (non-zero-rate bit set) sites."""
+        buf = np.zeros(6, np.uint64)
+        N.check(self._lib.aec_net_sweep_stats(self._h, _ptr(buf)))
+        v = [int(x) for x in buf]
+        return {"nz_groups": v[0], "groups": v[1], "live_conv_elems": v[2], "conv_elems": v[3], "live_pool_elems": v[4],
+                "pool_elems": v[5]}
+
+    def tc_layers(self):
+        """Indices of the conv layers that run on the tensor-core kernel (previous layer a map with C % 4 == 0, kh*kw <= 32)."""
+        out = []
+        for i, info in enumerate(self.infos):
+            if info.type == N.AEC_LAYER_CONV and i > 1 and info.in_channels % 4 == 0 and info.k_h * info.k_w <= 32:
+                out.append(i)
+        return out
+
     TC_TIMING_SLOTS = ("mma_total", "mma_wait_acc", "mma_wait_sites", "mma_wait_weights", "prod_total", "prod_wait_siteinfo",
                        "prod_wait_stage", "epi_total", "epi_wait_acc", "epi_wait_siteinfo", "load_total", "load_wait", "ctas", "units",
                        "gate_wait_sites")

@@ -172,12 +172,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(net, sites_per_step, nz_fraction, streams, batch):
-    """SURVEY 8(d) / BASELINE.md section 4 per step over all streams, with the leak term stated for what
-    the algorithm needs: A is read everywhere (4 B/elem), F is read and written only where A != 0."""
+def algorithmic_bytes(net, sites_per_step, sw, streams, batch):
+    """SURVEY 8(d) / BASELINE.md section 4 per step over all streams, with the leak term stated for what the
+    implemented algorithm needs: the rate A is read at the sites whose non-zero-rate bit is set (4 B/elem),
+    F is read and written only in the 16-byte groups whose rate is non-zero (8 B/elem), plus the bitmaps.
+    The pool layers' (Fp, Ap) copies are an implementation choice and are NOT counted as algorithmic."""
     shapes = net.shapes()
-    e_conv = sum(c * h * w for nm, (c, h, w) in zip(net.names, shapes) if "conv" in nm)
-    leak = streams * e_conv * (4 + 8 * nz_fraction)
+    nz4 = sw["nz_groups"] / max(1, sw["groups"])
+    bitmaps = sum(h * ((w + 31) // 32) * 4 for nm, (c, h, w) in zip(net.names, shapes) if "conv" in nm) * streams
+    leak = 4.0 * sw["live_conv_elems"] + 8.0 * nz4 * sw["conv_elems"] + bitmaps
     surface = streams * 2 * 8 * H * W
     ev = streams * 12 * batch
     conv = pool = 0.0
@@ -192,6 +195,16 @@ def algorithmic_bytes(net, sites_per_step, nz_fraction, streams, batch):
             pool += n * c * 36
     return {"leak_sweep": leak, "surface": surface, "conv": conv, "pool": pool, "events": ev,
             "total": leak + surface + conv + pool + ev}
+
+
+def conv_flops(net, sites_per_step, layers):
+    """Useful FLOPs per step of the gathered GEMM over `layers`: sites x {value, rate} x 2 x K x Cout."""
+    shapes = net.shapes()
+    fl = 0.0
+    for i in layers:
+        info = net.infos[i]
+        fl += float(sites_per_step[i]) * 2 * 2 * info.k_h * info.k_w * info.in_channels * shapes[i][0]
+    return fl
 
 
 def native_arm(args):
@@ -271,7 +284,7 @@ def native_arm(args):
     value = world * S * B * K / (ms_total * 1e-3)
 
     # ---- per-kernel durations inside the real step (events after every launch), same K steps again
-    nz_frac, _ = net.nonzero_rate_fraction()
+    sw = net.sweep_stats()
     net.profile(True)
     for _ in range(K):
         gpu_step(t)
@@ -279,14 +292,16 @@ def native_arm(args):
     prof, psteps = net.read_profile()
     net.profile(False)
     step_ms_prof = sum(prof.values())
+    tc_layers = net.tc_layers()
+    tc_names = {net.names[i] + ".eval" for i in tc_layers}
     by_kernel = {}
     for name, ms in prof.items():
         key = name.split(".")[-1] if "." in name else name
         key = {"frontier": "frontier_bitmaps", "eval": "site_eval"}.get(key, key)
         if key == "site_eval":
-            key = "conv_eval" if "conv" in name else "pool_eval"
+            key = ("conv_eval_tc" if name in tc_names else "conv_eval_simt") if "conv" in name else "pool_eval"
         by_kernel[key] = by_kernel.get(key, 0.0) + ms
-    ab = algorithmic_bytes(net, sites_per_step, nz_frac, S, B)
+    ab = algorithmic_bytes(net, sites_per_step, sw, S, B)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -294,18 +309,48 @@ def native_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    sweep_ms = prof.get("leak_sweep", 0.0)
-    achieved = ab["leak_sweep"] / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_leak_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab["leak_sweep"], "kernel_ms": sweep_ms,
-                "kernel_share_of_step": sweep_ms / step_ms_prof if step_ms_prof else None,
-                "nonzero_rate_fraction": nz_frac,
-                "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms_total / K * 1e-3) / 1e9,
-                               "frac": ab["total"] / (ms_total / K * 1e-3) / 1e9 / peak},
+    # dominant kernel of the step: the gathered GEMM on the tensor cores (k_conv_eval_tc, one launch per conv layer)
+    tc_ms = by_kernel.get("conv_eval_tc", 0.0)
+    fl = conv_flops(net, sites_per_step, tc_layers)
+    bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tf32_peak = bf16 / 2.0
+    tc_tflops = fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    n_tc = max(1, len(tc_layers))
+    roofline = {"bound": "tensor", "kernel": "k_conv_eval_tc", "achieved": tc_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": tc_tflops / tf32_peak, "traffic": None,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s bf16 / 2")
+                + " (kind::tf32 runs at half the bf16 rate; the kernel is timed inside a long step, so the sustained figure)",
+                "precision": "3xTF32 (three tcgen05.mma per product for fp32-grade results): the ceiling for useful FLOPs is peak / 3",
+                "frac_of_3xtf32_ceiling": 3.0 * tc_tflops / tf32_peak,
+                "algorithmic_flops_per_launch": fl / n_tc, "launches_per_step": len(tc_layers), "kernel_ms": tc_ms / n_tc,
+                "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                 "ms_by_kernel": {k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
                 "ms_by_launch": {k: round(v, 4) for k, v in prof.items()},
                 "sites_per_step_per_stream": {nm: round(float(sites_per_step[i]) / S, 1) for i, nm in enumerate(net.names) if i}}
+    # DRAM traffic per launch from the committed ncu --set full capture of the same workload (profiles/traffic.json)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        same = (tj["config"]["streams_per_gpu"] == S and tj["config"]["stream_kind"] == args.kind and tj["config"]["batch_event_size"] == B)
+    except Exception:
+        tj, same = None, False
+    if same:
+        roofline["traffic"] = tj["dram_bytes_per_launch"].get("k_conv_eval_tc")
+        roofline["traffic_source"] = tj["source"]
+    # the dominant HBM-bound kernel: the leak sweep
+    sweep_ms = prof.get("leak_sweep", 0.0)
+    achieved = ab["leak_sweep"] / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline_hbm = {"bound": "hbm", "kernel": "k_leak_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ab["leak_sweep"], "kernel_ms": sweep_ms,
+                    "kernel_share_of_step": sweep_ms / step_ms_prof if step_ms_prof else None,
+                    "live_site_fraction": sw["live_conv_elems"] / max(1, sw["conv_elems"]),
+                    "nonzero_rate_group_fraction": sw["nz_groups"] / max(1, sw["groups"]),
+                    "unaccounted": "the pool layers' (Fp, Ap) copies swept by the same launch (live %.3g of %.3g elements x 12 B) are not in the algorithmic bytes" % (
+                        sw["live_pool_elems"], sw["pool_elems"]),
+                    "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms_total / K * 1e-3) / 1e9,
+                                   "frac": ab["total"] / (ms_total / K * 1e-3) / 1e9 / peak}}
+    if same:
+        roofline_hbm["traffic"] = tj["dram_bytes_per_launch"].get("k_leak_sweep")
 
     # ---- end to end through the public host API: pinned host events in, head out, every step
     ev_host = torch.from_numpy(ev_np[t:t + n_e2e]).pin_memory()
@@ -333,7 +378,7 @@ def native_arm(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, S),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(evh[0].nbytes + offh.nbytes),
                     "d2h_bytes_per_step": int(headh.nbytes + 4), "ms_per_step": 1e3 * e2e_s / (n_e2e - 1), "head_abs_sum": checksum},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "state_bytes_per_stream": net.state_bytes_per_stream(), "device_bytes": net.device_bytes(),
         }
         if cpu is not None:

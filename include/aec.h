@@ -205,6 +205,14 @@ int aec_net_read_profile(aec_net *net, double *ms_per_slot, int n_slots, unsigne
 int aec_net_count_nonzero_rate_groups(aec_net *net, unsigned long long *nz_groups, unsigned long long *total_groups);
 
 /*
+ * Measurement helper for the leak sweep's roofline.  out6 = { 16-byte groups of the conv rate maps holding a
+ * non-zero rate, all such groups, conv-map elements at sites whose non-zero-rate bit is set (the elements
+ * whose rate the sweep has to read), all conv-map elements, the same two for the pool layers' (Fp, Ap)
+ * copies }.  Synchronises.
+ */
+int aec_net_sweep_stats(aec_net *net, unsigned long long *out6);
+
+/*
  * Measurement helper for the tensor-core conv kernel: with out16 == NULL, enables (enable != 0) or
  * disables per-role cycle accounting and clears the counters; with out16 != NULL copies the 16
  * counters of conv layer `layer` (summed over CTAs and launches since enabling: MMA-warp total /
