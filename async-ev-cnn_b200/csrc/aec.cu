@@ -56,7 +56,7 @@ struct HostLayer {
     float *wgt = nullptr, *bias = nullptr;
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
     bool tc = false;
-    int KB = 0, Mrows = 0, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
+    int KB = 0, Mrows = 0, Mch = 0, rep = 1, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
@@ -81,6 +81,17 @@ struct aec_net {
     size_t head_per_stream = 0;
     int32_t *ev_dev = nullptr, *off_dev = nullptr;
     size_t ev_cap = 0;
+    // pipelined host stepping (aec_net_step_host_async): two slots of event staging / head buffers, copy streams
+    struct HostSlot {
+        int32_t *ev = nullptr, *off = nullptr;
+        size_t ev_cap = 0;
+        float *head = nullptr;
+        cudaEvent_t ev_ready = nullptr, k_done = nullptr, d2h_done = nullptr;
+        bool used = false;
+    } slot[2];
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    unsigned long long async_calls = 0;
+    float *head_cur = nullptr;     // where k_head writes (n->head, or a slot's buffer)
     int num_sms = 148;
     int sweep_chunks = 0, sweep_nconv = 0, sweep_conv_chunks = 0;
     SweepParams sweep_all;
@@ -191,7 +202,11 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
     if (!l.tc) return;
     const int c8 = (l.C + 7) / 8 * 8;
     l.m_tiles = (c8 + 127) / 128;
-    l.Mrows = ((c8 + l.m_tiles - 1) / l.m_tiles + 7) / 8 * 8;      // output channels per weight tile (<= 128)
+    l.Mch = ((c8 + l.m_tiles - 1) / l.m_tiles + 7) / 8 * 8;        // output channels per weight tile (<= 128)
+    l.rep = 1;                                                      // copies of the channels along M (narrow layers: parallel epilogue)
+    if (l.m_tiles == 1 && l.Mch == 32) l.rep = 4;                   // measured: pays for 32 channels (one live epilogue warp otherwise); for 64
+                                                                    // the larger weight stages (2 instead of 4 in flight) cost more than they give
+    l.Mrows = l.Mch * l.rep;
     l.mtu = std::min(l.m_tiles, tc::kMaxMtu);
     l.n_acc = l.mtu == 1 ? 2 : 1;
     l.KB = (l.K + tc::kBlockK - 1) / tc::kBlockK;
@@ -199,7 +214,7 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
     const size_t budget = 210 * 1024;        // 227 KB per CTA minus ~15 KB static shared memory and the 1 KB alignment slack
     l.w_stages = (int)std::min<size_t>(tc::kMaxWStages, std::max<size_t>(2, (budget - x_bytes) / w_stage));
     l.tc_smem = x_bytes + (size_t)l.w_stages * w_stage + 1024;
-    if ((size_t)l.h_b.size() < (size_t)l.Mrows * l.m_tiles) l.h_b.resize((size_t)l.Mrows * l.m_tiles, 0.f);
+    if ((size_t)l.h_b.size() < (size_t)l.Mch * l.m_tiles) l.h_b.resize((size_t)l.Mch * l.m_tiles, 0.f);
     // image: [weight tile][K block][hi | lo][row = channel within the tile][32 floats, 16-byte chunks XOR-swizzled by row & 7]
     l.h_wimg.assign((size_t)l.m_tiles * l.KB * 2 * l.Mrows * tc::kBlockK, 0.f);
     for (int mt = 0; mt < l.m_tiles; ++mt)
@@ -207,7 +222,7 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
             for (int r = 0; r < l.Mrows; ++r)
                 for (int j = 0; j < 8; ++j)
                     for (int e = 0; e < 4; ++e) {
-                        const int k = kb * tc::kBlockK + 4 * j + e, col = mt * l.Mrows + r;
+                        const int k = kb * tc::kBlockK + 4 * j + e, col = mt * l.Mch + r % l.Mch;
                         const float w = (k < l.K && col < l.C) ? kernel_hwio[(size_t)k * l.C + col] : 0.f;
                         float hi, lo;
                         split_tf32_host(w, &hi, &lo);
@@ -408,7 +423,7 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     p.src_stride = src.fstride; p.alpha = src.alpha;
     p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
     p.wimg = l.wimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
-    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.Mch = l.Mch; p.rep = l.rep; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
 
@@ -490,7 +505,7 @@ static int run_head(aec_net *n, cudaStream_t st)
 {
     HeadParams p;
     p.src = make_src(n, (int)n->L.size() - 1);
-    p.out = n->head;
+    p.out = n->head_cur ? n->head_cur : n->head;
     p.S = n->S;
     long long total = (long long)n->head_per_stream * n->S;
     int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
@@ -690,6 +705,16 @@ extern "C" void aec_net_destroy(aec_net *n)
     cudaDeviceSynchronize();
     for (void *p : n->allocs) cudaFree(p);
     if (n->ev_dev) cudaFree(n->ev_dev);
+    for (auto &sl : n->slot) {
+        if (sl.ev) cudaFree(sl.ev);
+        if (sl.off) cudaFree(sl.off);
+        if (sl.head) cudaFree(sl.head);
+        if (sl.ev_ready) cudaEventDestroy(sl.ev_ready);
+        if (sl.k_done) cudaEventDestroy(sl.k_done);
+        if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+    }
+    if (n->h2d) cudaStreamDestroy(n->h2d);
+    if (n->d2h) cudaStreamDestroy(n->d2h);
     delete n;
 }
 
@@ -780,6 +805,67 @@ extern "C" int aec_net_step_host(aec_net *n, const int32_t *ev, const int32_t *o
     if (head_out)
         CU(cudaMemcpyAsync(head_out, n->head, (size_t)n->S * n->head_per_stream * sizeof(float), cudaMemcpyDeviceToHost, st));
     return check_err_flag(n, st);
+}
+
+extern "C" int aec_net_host_sync(aec_net *n, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (n->h2d) CU(cudaStreamSynchronize(n->h2d));
+    CU(cudaStreamSynchronize(st));
+    if (n->d2h) CU(cudaStreamSynchronize(n->d2h));
+    return check_err_flag(n, st);
+}
+
+extern "C" int aec_net_step_host_async(aec_net *n, const int32_t *ev, const int32_t *off, int total, float *head_out, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    if (total < 0 || !off || (total > 0 && !ev)) return fail(AEC_EINVAL, "bad event buffers");
+    if (n->profiling) return fail(AEC_ESTATE, "per-launch profiling is not available on the pipelined host path");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (!n->h2d) {
+        CU(cudaStreamCreateWithFlags(&n->h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&n->d2h, cudaStreamNonBlocking));
+    }
+    for (auto &s2 : n->slot) {                 // both slots are set up on the first call (allocation synchronises)
+        if (!s2.ev_ready) {
+            CU(cudaEventCreateWithFlags(&s2.ev_ready, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s2.k_done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s2.d2h_done, cudaEventDisableTiming));
+            CU(cudaMalloc(&s2.off, ((size_t)n->S + 1) * sizeof(int32_t)));
+            CU(cudaMalloc(&s2.head, (size_t)n->S * n->head_per_stream * sizeof(float)));
+        }
+        if ((size_t)total > s2.ev_cap) {       // grow the staging buffers: nothing may still be reading them
+            int rc = aec_net_host_sync(n, cuda_stream);
+            if (rc && rc != AEC_EEVENTS) return rc;
+            if (s2.ev) { CU(cudaFree(s2.ev)); s2.ev = nullptr; }
+            const size_t cap = std::max<size_t>((size_t)total * 3 / 2, 1024);
+            CU(cudaMalloc(&s2.ev, cap * 3 * sizeof(int32_t)));
+            s2.ev_cap = cap;
+        }
+    }
+    aec_net::HostSlot &sl = n->slot[n->async_calls & 1];
+    // copy-in stream: the kernels of this slot's previous step must have consumed its events
+    if (sl.used) CU(cudaStreamWaitEvent(n->h2d, sl.k_done, 0));
+    if (total > 0) CU(cudaMemcpyAsync(sl.ev, ev, (size_t)total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, n->h2d));
+    CU(cudaMemcpyAsync(sl.off, off, ((size_t)n->S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, n->h2d));
+    CU(cudaEventRecord(sl.ev_ready, n->h2d));
+    // compute stream: events in place, this slot's head buffer read back
+    CU(cudaStreamWaitEvent(st, sl.ev_ready, 0));
+    if (sl.used) CU(cudaStreamWaitEvent(st, sl.d2h_done, 0));
+    n->head_cur = sl.head;
+    int rc = aec_net_step_device(n, sl.ev, sl.off, total, cuda_stream);
+    n->head_cur = nullptr;
+    if (rc) return rc;
+    CU(cudaEventRecord(sl.k_done, st));
+    // copy-out stream
+    CU(cudaStreamWaitEvent(n->d2h, sl.k_done, 0));
+    if (head_out)
+        CU(cudaMemcpyAsync(head_out, sl.head, (size_t)n->S * n->head_per_stream * sizeof(float), cudaMemcpyDeviceToHost, n->d2h));
+    CU(cudaEventRecord(sl.d2h_done, n->d2h));
+    sl.used = true;
+    n->async_calls++;
+    return AEC_OK;
 }
 
 extern "C" const float *aec_net_head_device(const aec_net *n) { return n ? n->head : nullptr; }

@@ -180,7 +180,10 @@ struct TcParams {
     int C, H, W;                // output map
     int K, KB;                  // contraction length, number of 32-wide K blocks
     int ks_last;                // 8-wide MMA steps of the last K block: ceil((K - 32*(KB-1)) / 8), the rest is padding
-    int Mrows, m_tiles;         // output channels per weight tile (multiple of 8, <= 128), weight tiles
+    int Mrows, m_tiles;         // rows per weight tile (multiple of 8, <= 128) = Mch * rep, weight tiles
+    int Mch, rep;               // output channels per weight tile; rep (1, 2, 4) copies of them along M so that the
+                                // epilogue of a narrow layer spreads over rep x Mch/32 warps (copy g stores the 16-column
+                                // chunks with chunk % rep == g; the extra rows cost the tensor core nothing, M is 128 anyway)
     int mtu;                    // weight tiles per unit (1 or 2): the unit's sites are gathered once for all of them
     int kh, kw, pad_t, pad_l;
     int w_stages;               // weight pipeline depth
@@ -376,7 +379,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             tc_fence_after();
             if (warp_live) {
                 for (int mt = 0; mt < mt_count; ++mt) {
-                    const int c = (mg * p.mtu + mt) * p.Mrows + row;
+                    const int g = p.rep > 1 ? (warp * 32) / p.Mch : 0;    // which copy of the channels this warp holds (Mch % 32 == 0 when rep > 1)
+                    const int c = (mg * p.mtu + mt) * p.Mch + (row - g * p.Mch);
                     const bool c_ok = row < p.Mrows && c < p.C && !(p.debug & 8);
                     const long long a_minus_f = (const char *)p.A - (const char *)p.F;
                     const float bias = c_ok ? __ldg(p.bias + c) : 0.f;
@@ -398,15 +402,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                             if (o.y >= 0) *reinterpret_cast<float *>(base + o.y) = is_rate ? v1 : __fadd_rn(v1, add);
                         }
                     };
-                    tmem_ld16(taddr, ra);
+                    const int cstep = 16 * p.rep;                         // this copy's chunks: cc = 16g, 16g + cstep, ...
+                    tmem_ld16(taddr + (uint32_t)(16 * g), ra);
 #pragma unroll 1
-                    for (int cc = 0; cc < kUnitCols; cc += 32) {
+                    for (int cc = 16 * g; cc < kUnitCols; cc += 2 * cstep) {
                         tmem_ld_wait();
-                        tmem_ld16(taddr + (uint32_t)(cc + 16), rb);
+                        if (cc + cstep < kUnitCols) tmem_ld16(taddr + (uint32_t)(cc + cstep), rb);
                         store16(ra, cc);
+                        if (cc + cstep >= kUnitCols) break;
                         tmem_ld_wait();
-                        if (cc + 32 < kUnitCols) tmem_ld16(taddr + (uint32_t)(cc + 32), ra);
-                        store16(rb, cc + 16);
+                        if (cc + 2 * cstep < kUnitCols) tmem_ld16(taddr + (uint32_t)(cc + 2 * cstep), ra);
+                        store16(rb, cc + cstep);
                     }
                 }
             }

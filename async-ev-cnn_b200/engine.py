@@ -138,6 +138,19 @@ class EventNetCuda:
             self._raise_events(e)
         return out
 
+    def step_packed_async(self, events, offsets, out, cuda_stream=None):
+        """Pipelined host step (aec_net_step_host_async): returns once enqueued.  `events`, `offsets`, `out` must be
+        C-contiguous int32 / int32 / float32 arrays (pinned for real overlap) that stay untouched until host_sync()."""
+        assert events.dtype == np.int32 and offsets.dtype == np.int32 and out.dtype == np.float32
+        assert events.flags.c_contiguous and offsets.flags.c_contiguous and out.flags.c_contiguous
+        N.check(self._lib.aec_net_step_host_async(self._h, _ptr(events), _ptr(offsets), int(offsets[-1]), _ptr(out), cuda_stream))
+
+    def host_sync(self, cuda_stream=None):
+        try:
+            N.check(self._lib.aec_net_host_sync(self._h, cuda_stream))
+        except N.AecError as e:
+            self._raise_events(e)
+
     def step(self, per_stream_events, out=None):
         """per_stream_events: list (length n_streams) of int32 [B_s,3] arrays, or one array when n_streams == 1."""
         if isinstance(per_stream_events, np.ndarray) and per_stream_events.ndim == 2:

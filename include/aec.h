@@ -143,6 +143,20 @@ int aec_net_step_device(aec_net *net, const int32_t *events_yxt, const int32_t *
 int aec_net_step_host(aec_net *net, const int32_t *events_yxt, const int32_t *offsets, int total_events,
                       float *head_out, void *cuda_stream);
 
+/*
+ * Pipelined form of aec_net_step_host for throughput: enqueues the host->device copy of the events on an
+ * internal copy-in stream, the step on `cuda_stream` and the device->host copy of the head on an internal
+ * copy-out stream, and returns without waiting.  Two steps can be in flight (two staging slots), so the
+ * copies of step t+1 / t-1 overlap the kernels of step t.  The host buffers of a call (events, offsets,
+ * head_out - use pinned memory) must stay valid and unmodified, and head_out unread, until
+ * aec_net_host_sync() returns; consecutive calls must use different head_out buffers.
+ * aec_net_host_sync waits for everything enqueued and returns AEC_EEVENTS if any of those steps skipped
+ * out-of-range events or over-long streams.
+ */
+int aec_net_step_host_async(aec_net *net, const int32_t *events_yxt, const int32_t *offsets, int total_events,
+                            float *head_out, void *cuda_stream);
+int aec_net_host_sync(aec_net *net, void *cuda_stream);
+
 /* Device pointer / element count of the head buffer written by the last step. */
 const float *aec_net_head_device(const aec_net *net);
 size_t aec_net_head_elems_per_stream(const aec_net *net);

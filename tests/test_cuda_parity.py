@@ -172,3 +172,31 @@ def test_event_vs_frame_equivalence_on_gpu():
             fm = net.view(i, 0, which=("featuremap",))["featuremap"]
             assert np.allclose(fm, d, rtol=1e-5, atol=1e-5), "step %d layer %s" % (s, net.names[i])
     net.close()
+
+
+def test_pipelined_host_steps_equal_blocking_steps():
+    """aec_net_step_host_async (two steps in flight, separate copy streams) == aec_net_step_host, bit for bit."""
+    g = Golden(golden_path("small32_float"))
+    S, steps = 3, 24
+    a = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=S)
+    b = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=S)
+    from async_ev_cnn_b200.engine import pack_events
+    packed = [pack_events([g.events(t), g.events(t) if t % 3 else None, g.events((t + 5) % g.n_steps)]) for t in range(steps)]
+    want = [a.step_packed(ev, off).copy() for ev, off in packed]
+    outs = [np.empty_like(want[0]) for _ in range(steps)]
+    for t, (ev, off) in enumerate(packed):
+        b.step_packed_async(ev, off, outs[t])
+        if t % 5 == 4:
+            b.host_sync()
+    b.host_sync()
+    for t in range(steps):
+        assert np.array_equal(outs[t], want[t]), "step %d" % t
+    for li in range(len(a.names)):
+        sa, sb = a.state(li, 2), b.state(li, 2)
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k])
+    with pytest.raises(IndexError):
+        b.step_packed_async(np.array([[g.height, 0, 5]], np.int32), np.array([0, 1, 1, 1], np.int32), outs[0])
+        b.host_sync()
+    a.close()
+    b.close()
