@@ -475,6 +475,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     HostLayer &l = n->L[li];
     const HostLayer &pv = n->L[li - 1];
     int rc;
+    if (with_sweep) CU(cudaMemsetAsync(n->counts + li, 0, sizeof(int), st));   // layer-at-a-time: the call may be repeated within a step
     if (l.type == AEC_LAYER_CONV) {
         if (with_sweep && (rc = run_sweep(n, li, st))) return rc;
         ConvFrontParams p;
