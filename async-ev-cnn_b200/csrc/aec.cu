@@ -6,6 +6,7 @@
 #include "../../include/aec.h"
 #include "aec_kernels.cuh"
 #include "aec_tc.cuh"
+#include "aec_frontend.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -92,6 +93,10 @@ struct aec_net {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     unsigned long long async_calls = 0;
     float *head_cur = nullptr;     // where k_head writes (n->head, or a slot's buffer)
+    float *dec_boxes = nullptr, *dec_conf = nullptr;   // aec_net_decode_head scratch
+    int32_t *dec_label = nullptr;
+    uint8_t *dec_valid = nullptr;
+    size_t dec_cap = 0;
     int num_sms = 148;
     int sweep_chunks = 0, sweep_nconv = 0, sweep_conv_chunks = 0;
     SweepParams sweep_all;
@@ -714,6 +719,7 @@ extern "C" void aec_net_destroy(aec_net *n)
         if (sl.k_done) cudaEventDestroy(sl.k_done);
         if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
     }
+    if (n->dec_boxes) { cudaFree(n->dec_boxes); cudaFree(n->dec_conf); cudaFree(n->dec_label); cudaFree(n->dec_valid); }
     if (n->h2d) cudaStreamDestroy(n->h2d);
     if (n->d2h) cudaStreamDestroy(n->d2h);
     delete n;
@@ -1079,4 +1085,89 @@ extern "C" int aec_net_sweep_stats(aec_net *n, unsigned long long *out6)
     CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
     out6[2] = live_conv; out6[3] = all_conv; out6[4] = live_pool; out6[5] = all_pool;
     return AEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// front end / back end of the path
+extern "C" int aec_net_decode_head(aec_net *n, int num_classes, int num_bbox, int h_cells, int w_cells, int h_image, int w_image,
+                                   float conf_threshold, float *boxes_out, float *conf_out, int32_t *label_out, uint8_t *valid_out,
+                                   void *cuda_stream)
+{
+    NEED_FINAL(n);
+    if (num_classes < 1 || num_bbox < 1 || h_cells < 1 || w_cells < 1)
+        return fail(AEC_EINVAL, "decode_head: bad grid / class / box counts");
+    if ((size_t)h_cells * w_cells * (num_classes + 5 * num_bbox) != n->head_per_stream)
+        return fail(AEC_EINVAL, "decode_head: %dx%dx(%d+5*%d) does not match the head of %zu values per stream", h_cells, w_cells,
+                    num_classes, num_bbox, n->head_per_stream);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t nb = (size_t)n->S * h_cells * w_cells * num_bbox;
+    if (nb > n->dec_cap) {
+        CU(cudaStreamSynchronize(st));
+        if (n->dec_boxes) { cudaFree(n->dec_boxes); cudaFree(n->dec_conf); cudaFree(n->dec_label); cudaFree(n->dec_valid); }
+        CU(cudaMalloc(&n->dec_boxes, nb * 4 * sizeof(float)));
+        CU(cudaMalloc(&n->dec_conf, nb * sizeof(float)));
+        CU(cudaMalloc(&n->dec_label, nb * sizeof(int32_t)));
+        CU(cudaMalloc(&n->dec_valid, nb));
+        n->dec_cap = nb;
+    }
+    DecodeParams p;
+    p.head = n->head; p.boxes = n->dec_boxes; p.conf = n->dec_conf; p.label = n->dec_label; p.valid = n->dec_valid;
+    p.S = n->S; p.gh = h_cells; p.gw = w_cells; p.C = num_classes; p.B = num_bbox; p.h_img = h_image; p.w_img = w_image;
+    p.thr = conf_threshold;
+    const int blocks = (int)std::min<size_t>((nb + kThreads - 1) / kThreads, (size_t)n->num_sms * 8);
+    k_decode_head<<<blocks, kThreads, 0, st>>>(p);
+    int rc = launch_check(n, "k_decode_head");
+    if (rc) return rc;
+    if (boxes_out) CU(cudaMemcpyAsync(boxes_out, n->dec_boxes, nb * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (conf_out) CU(cudaMemcpyAsync(conf_out, n->dec_conf, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (label_out) CU(cudaMemcpyAsync(label_out, n->dec_label, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, n->dec_valid, nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AEC_OK;
+}
+
+extern "C" int aec_decode_ndata(int device, const uint8_t *raw, const long long *byte_offsets, int n_recordings, int zero_base_ts,
+                                int crop, int new_h, int new_w, int32_t *events_yxt_out, int32_t *polarity_out, int32_t *counts_out)
+{
+    if (!byte_offsets || n_recordings < 0 || !counts_out) return fail(AEC_EINVAL, "decode_ndata: bad arguments");
+    if (n_recordings == 0) return AEC_OK;
+    for (int r = 0; r < n_recordings; ++r)
+        if (byte_offsets[r + 1] < byte_offsets[r] || byte_offsets[r] % 5 || byte_offsets[r + 1] % 5)
+            return fail(AEC_EINVAL, "decode_ndata: recording %d is not a whole number of 5-byte records", r);
+    const long long total_bytes = byte_offsets[n_recordings];
+    if (total_bytes > 0 && (!raw || !events_yxt_out)) return fail(AEC_EINVAL, "decode_ndata: NULL buffers");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(AEC_EINVAL, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    const long long n_ev = total_bytes / 5;
+    uint8_t *d_raw = nullptr;
+    long long *d_off = nullptr;
+    int32_t *d_ev = nullptr, *d_pol = nullptr, *d_cnt = nullptr;
+    int rc = AEC_OK;
+    auto cleanup = [&]() { cudaFree(d_raw); cudaFree(d_off); cudaFree(d_ev); cudaFree(d_pol); cudaFree(d_cnt); };
+#define CUF(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { cleanup(); return fail(AEC_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    CUF(cudaMalloc(&d_raw, std::max<long long>(total_bytes, 1)));
+    CUF(cudaMalloc(&d_off, ((size_t)n_recordings + 1) * sizeof(long long)));
+    CUF(cudaMalloc(&d_ev, std::max<long long>(n_ev, 1) * 3 * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_pol, std::max<long long>(n_ev, 1) * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_cnt, (size_t)n_recordings * sizeof(int32_t)));
+    if (total_bytes) CUF(cudaMemcpy(d_raw, raw, (size_t)total_bytes, cudaMemcpyHostToDevice));
+    CUF(cudaMemcpy(d_off, byte_offsets, ((size_t)n_recordings + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    NdataParams p;
+    p.raw = d_raw; p.byte_off = d_off; p.events = d_ev; p.polarity = polarity_out ? d_pol : nullptr; p.counts = d_cnt;
+    p.zero_base = zero_base_ts; p.crop = crop; p.new_h = new_h; p.new_w = new_w;
+    k_ndata_decode<<<n_recordings, kThreads>>>(p);
+    CUF(cudaGetLastError());
+    CUF(cudaDeviceSynchronize());
+    if (n_ev) CUF(cudaMemcpy(events_yxt_out, d_ev, (size_t)n_ev * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (n_ev && polarity_out) CUF(cudaMemcpy(polarity_out, d_pol, (size_t)n_ev * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUF(cudaMemcpy(counts_out, d_cnt, (size_t)n_recordings * sizeof(int32_t), cudaMemcpyDeviceToHost));
+#undef CUF
+    cleanup();
+    return rc;
 }

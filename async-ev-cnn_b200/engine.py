@@ -163,6 +163,19 @@ class EventNetCuda:
         N.check(self._lib.aec_net_step_device(self._h, ctypes.c_void_p(events_ptr), ctypes.c_void_p(offsets_ptr),
                                               int(total), cuda_stream))
 
+    def decode_head(self, num_classes, num_bbox, h_cells, w_cells, conf_threshold=0.1, h_image=None, w_image=None):
+        """YOLO decode of the last step's head on the device (viz.py:27-46,131-148): returns boxes [S, cells*B, 4]
+        (x, y, w, h in pixels), conf [S, cells*B], valid bool, label int32 - what viz.draw_bboxes draws from."""
+        nb = h_cells * w_cells * num_bbox
+        boxes = np.empty((self.n_streams, nb, 4), np.float32)
+        conf = np.empty((self.n_streams, nb), np.float32)
+        label = np.empty((self.n_streams, nb), np.int32)
+        valid = np.empty((self.n_streams, nb), np.uint8)
+        N.check(self._lib.aec_net_decode_head(self._h, int(num_classes), int(num_bbox), int(h_cells), int(w_cells),
+                                              int(h_image or self.height), int(w_image or self.width), float(conf_threshold),
+                                              _ptr(boxes), _ptr(conf), _ptr(label), _ptr(valid), None))
+        return boxes, conf, valid.astype(bool), label
+
     def head_device_ptr(self):
         return int(self._lib.aec_net_head_device(self._h))
 

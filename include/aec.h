@@ -219,6 +219,32 @@ int aec_net_read_profile(aec_net *net, double *ms_per_slot, int n_slots, unsigne
 int aec_net_count_nonzero_rate_groups(aec_net *net, unsigned long long *nz_groups, unsigned long long *total_groups);
 
 /*
+ * The step after the path: YOLO decode of the head left by the last step
+ * (src/libs/viz.py:27-46 convert_bboxes with sqrt = True, and the decode half of draw_bboxes :131-148,165).
+ * The head of every stream is read as [h_cells][w_cells][num_classes + 5*num_bbox].  HOST outputs, any may be
+ * NULL: boxes float32 [n_streams][h_cells*w_cells*num_bbox][4] = (x, y, w, h) in pixels of an h_image x w_image
+ * frame, conf float32 [..], label int32 [..] = argmax over classes of class*conf, valid uint8 [..] =
+ * conf > conf_threshold.  Float32 arithmetic in the reference's order (bit-exact).  Synchronises.
+ * Non-maximum suppression (src/libs/utils.py:38-118) stays on the host.
+ */
+int aec_net_decode_head(aec_net *net, int num_classes, int num_bbox, int h_cells, int w_cells, int h_image, int w_image,
+                        float conf_threshold, float *boxes_out, float *conf_out, int32_t *label_out, uint8_t *valid_out,
+                        void *cuda_stream);
+
+/*
+ * The step before the path (SURVEY 8f, f3 + f1): decodes N-MNIST / N-Caltech101 recordings - 5 bytes per event,
+ * x, y, polarity bit + 23-bit timestamp, records with y == 240 are timestamp-overflow markers
+ * (src/readers/file_reader.py:36-58) - and applies the runner's per-sample transform (src/libs/runner.py:24-33):
+ * zero-based timestamps (zero_base_ts != 0) and the centre crop of src/libs/utils.py:4-28 to new_h x new_w
+ * (crop != 0).  `raw` holds all recordings back to back, recording r = bytes [byte_offsets[r], byte_offsets[r+1]).
+ * Outputs (HOST): events (y, x, ts) int32 triples and polarity (may be NULL); recording r's events start at
+ * event index byte_offsets[r] / 5 and counts_out[r] of them are valid.  Stand-alone (no network object);
+ * synchronises the device.
+ */
+int aec_decode_ndata(int device, const uint8_t *raw, const long long *byte_offsets, int n_recordings, int zero_base_ts,
+                     int crop, int new_h, int new_w, int32_t *events_yxt_out, int32_t *polarity_out, int32_t *counts_out);
+
+/*
  * Measurement helper for the leak sweep's roofline.  out6 = { 16-byte groups of the conv rate maps holding a
  * non-zero rate, all such groups, conv-map elements at sites whose non-zero-rate bit is set (the elements
  * whose rate the sweep has to read), all conv-map elements, the same two for the pool layers' (Fp, Ap)

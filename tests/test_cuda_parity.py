@@ -200,3 +200,48 @@ def test_pipelined_host_steps_equal_blocking_steps():
         b.host_sync()
     a.close()
     b.close()
+
+
+def test_decode_head_kernel_equals_oracle():
+    from oracle import frontend as F
+    g = Golden(golden_path("efcn_edge"))
+    net = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=3)
+    for s in range(6):
+        heads = net.step([g.events(s), g.events(s + 1), None]).copy()
+    C, B, gh, gw = 100, 2, 5, 7
+    boxes, conf, valid, label = net.decode_head(C, B, gh, gw, conf_threshold=0.1)
+    ob, oc, ov, ol = F.decode_head(heads, gh, gw, C, g.height, g.width, 0.1)
+    assert np.array_equal(boxes, ob) and np.array_equal(conf, oc) and np.array_equal(valid, ov) and np.array_equal(label, ol)
+    with pytest.raises(Exception):
+        net.decode_head(C, B, gh, gw + 1)
+    net.close()
+
+
+def test_ndata_decode_kernel_equals_oracle():
+    from oracle import frontend as F
+    from async_ev_cnn_b200.frontend import decode_ndata
+    rng = np.random.default_rng(11)
+    recs, want = [], {}
+    for r, n in enumerate([0, 1, 7, 255, 256, 257, 5000, 40000]):
+        x = rng.integers(0, 232, n).astype(np.int32)
+        y = rng.integers(0, 172, n).astype(np.int32)
+        ts = np.sort(rng.integers(0, 1 << 13, n)).astype(np.int32)
+        p = rng.integers(0, 2, n).astype(np.int32)
+        if n > 10:
+            y[rng.integers(0, n, max(1, n // 300))] = 240          # overflow markers, a few in a row sometimes
+            y[3:5] = 240
+        recs.append(F.encode_ndata(x, y, ts, p))
+    for crop in (None, (160, 224)):
+        for zero in (True, False):
+            got, pols = decode_ndata(recs, zero_base_ts=zero, crop_to=crop, with_polarity=True)
+            for r, raw in enumerate(recs):
+                n, x, y, ts, p = F.read_ndata(raw)
+                if zero and n:
+                    ts = ts - ts[0]
+                if crop is not None and n:
+                    x, y, ts, p = F.center_crop_events(x, y, ts, p, crop)
+                ev = np.stack([y, x, ts], axis=-1).astype(np.int32) if len(x) else np.zeros((0, 3), np.int32)
+                assert np.array_equal(got[r], ev), "recording %d crop %s zero %s" % (r, crop, zero)
+                assert np.array_equal(pols[r], np.asarray(p, np.int32).reshape(-1))
+    with pytest.raises(ValueError):
+        decode_ndata([np.zeros(7, np.uint8)])
