@@ -63,3 +63,27 @@ def test_efcn_event_equals_dense_torch_frame_network():
     scale = np.abs(dense).max()
     assert np.abs(head - dense).max() <= 1e-4 * scale, "event vs dense frame: %.3e (scale %.3e)" % (np.abs(head - dense).max(), scale)
     net.close()
+
+
+STRESS_LAYERS = ("conv1=3,3,1,16 conv1b=3,3,16,16 pool1=2,2 conv2=3,3,16,32 conv2b=3,3,32,32 pool2=2,2 conv3=3,3,32,64 pool3=2,2 "
+                 "conv4=3,3,64,128 pool4=2,2 conv5=3,3,128,256 pool5=2,2 conv6=1,1,256,512 conv7=1,1,512,110")
+
+
+def test_stress_config_davis346_deeper_variant_against_live_oracle():
+    """BASELINE config 5: DAVIS346-sized stream cropped to 256x320 (pooled dims must be even), high
+    event rate (1000 events per step), a deeper EFCN variant (two 3x3 convs in the first two stages).  The
+    reference has no such config; its layers are generic, so the oracle runs it."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from parity import OracleAdapter, compare_live
+    from async_ev_cnn_b200.engine import CudaAdapter
+    from oracle.event_oracle import OracleEventNet
+    h, w, steps = 256, 320, 10
+    wts = P.xavier_weights(STRESS_LAYERS, seed=3)
+    evs = P.synthetic_events("edge", 1, steps, 1000, h, w, seed=7)[0]
+    net = EventNetCuda(h, w, STRESS_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=2, max_events_per_step=4096)
+    ora = OracleEventNet(h, w, STRESS_LAYERS, wts, 5e-5, 0.1, "SAME")
+    mm = compare_live(CudaAdapter(net, stream=1), OracleAdapter(ora), list(evs), exact=False)
+    print("\n[parity] stress 256x320 deeper EFCN: %r" % mm)
+    assert net.head_shape == (8, 10, 110)
+    net.close()
