@@ -93,6 +93,20 @@ struct aec_net {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     unsigned long long async_calls = 0;
     float *head_cur = nullptr;     // where k_head writes (n->head, or a slot's buffer)
+    // CUDA graph of one step (27 launches replayed with one call; only the event pointers of the surface kernel and
+    // the output pointer of the head kernel change between replays and are patched in place)
+    struct StepGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t integ = nullptr, head = nullptr;
+        cudaKernelNodeParams integ_kp, head_kp;
+        IntegrateParams ip;
+        HeadParams hp;
+        unsigned long long launches = 0;
+        bool failed = false;
+    } sg;
+    cudaStream_t cap = nullptr;
+    int use_graph = -1;            // -1 unknown, 0 off (AEC_GRAPH=0), 1 on
     float *dec_boxes = nullptr, *dec_conf = nullptr;   // aec_net_decode_head scratch
     int32_t *dec_label = nullptr;
     uint8_t *dec_valid = nullptr;
@@ -365,7 +379,7 @@ static int prof_collect(aec_net *n, cudaStream_t st)
     return AEC_OK;
 }
 
-static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cudaStream_t st)
+static IntegrateParams integrate_params(aec_net *n, const int32_t *ev, const int32_t *off)
 {
     const HostLayer &l = n->L[0];
     IntegrateParams p;
@@ -373,6 +387,13 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
     p.front = l.front; p.alive = l.nzr; p.events = ev; p.offsets = off; p.layer_counts = n->counts; p.err_flag = n->err_flag;
     p.n_layers = (int)n->L.size();
     p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.leak = n->leak; p.max_events = n->max_events; p.hash_slots = n->hash_slots;
+    return p;
+}
+
+static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cudaStream_t st)
+{
+    const HostLayer &l = n->L[0];
+    const IntegrateParams p = integrate_params(n, ev, off);
     const size_t smem = (size_t)n->hash_slots * 8 + (size_t)l.H * l.Ww * 8;
     int rc;
     if ((rc = prof_mark(n, st))) return rc;
@@ -507,12 +528,18 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     return run_pool_eval(n, li, st);
 }
 
-static int run_head(aec_net *n, cudaStream_t st)
+static HeadParams head_params(aec_net *n, float *out)
 {
     HeadParams p;
     p.src = make_src(n, (int)n->L.size() - 1);
-    p.out = n->head_cur ? n->head_cur : n->head;
+    p.out = out;
     p.S = n->S;
+    return p;
+}
+
+static int run_head(aec_net *n, cudaStream_t st)
+{
+    const HeadParams p = head_params(n, n->head_cur ? n->head_cur : n->head);
     long long total = (long long)n->head_per_stream * n->S;
     int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
     k_head<<<blocks, kThreads, 0, st>>>(p);
@@ -720,6 +747,9 @@ extern "C" void aec_net_destroy(aec_net *n)
         if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
     }
     if (n->dec_boxes) { cudaFree(n->dec_boxes); cudaFree(n->dec_conf); cudaFree(n->dec_label); cudaFree(n->dec_valid); }
+    if (n->sg.exec) cudaGraphExecDestroy(n->sg.exec);
+    if (n->sg.graph) cudaGraphDestroy(n->sg.graph);
+    if (n->cap) cudaStreamDestroy(n->cap);
     if (n->h2d) cudaStreamDestroy(n->h2d);
     if (n->d2h) cudaStreamDestroy(n->d2h);
     delete n;
@@ -759,17 +789,89 @@ extern "C" int aec_net_reset(aec_net *n, const uint8_t *stream_mask, void *cuda_
     return reset_streams(n, m, st);
 }
 
+static int step_body(aec_net *n, const int32_t *ev, const int32_t *off, cudaStream_t st)
+{
+    int rc;
+    if ((rc = run_integrate(n, ev, off, st))) return rc;
+    if ((rc = run_sweep(n, -1, st))) return rc;
+    for (int li = 1; li < (int)n->L.size(); ++li)
+        if ((rc = run_layer(n, li, false, st))) return rc;
+    return run_head(n, st);
+}
+
+// Captures one step into a CUDA graph (on an internal stream: the caller's may be the legacy default stream, which
+// cannot capture) and remembers the two kernel nodes whose pointer arguments change between steps.
+static int build_step_graph(aec_net *n, const int32_t *ev, const int32_t *off)
+{
+    aec_net::StepGraph &g = n->sg;
+    if (!n->cap) CU(cudaStreamCreateWithFlags(&n->cap, cudaStreamNonBlocking));
+    const unsigned long long l0 = n->launches;
+    CU(cudaStreamBeginCapture(n->cap, cudaStreamCaptureModeThreadLocal));
+    int rc = step_body(n, ev, off, n->cap);
+    cudaError_t e = cudaStreamEndCapture(n->cap, &g.graph);
+    g.launches = n->launches - l0;
+    n->launches = l0;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(AEC_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    CU(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    size_t num = 0;
+    CU(cudaGraphGetNodes(g.graph, nullptr, &num));
+    std::vector<cudaGraphNode_t> nodes(num);
+    CU(cudaGraphGetNodes(g.graph, nodes.data(), &num));
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        CU(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        CU(cudaGraphKernelNodeGetParams(nd, &kp));
+        if (kp.func == (void *)k_integrate) { g.integ = nd; g.integ_kp = kp; }
+        if (kp.func == (void *)k_head) { g.head = nd; g.head_kp = kp; }
+    }
+    if (!g.integ || !g.head) return fail(AEC_ECUDA, "step graph: surface / head kernel node not found");
+    g.ip = integrate_params(n, ev, off);
+    g.hp = head_params(n, n->head_cur ? n->head_cur : n->head);
+    return AEC_OK;
+}
+
 extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t *off, int total, void *cuda_stream)
 {
     NEED_FINAL(n);
     (void)total;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc;
-    if ((rc = run_integrate(n, ev, off, st))) return rc;
-    if ((rc = run_sweep(n, -1, st))) return rc;
-    for (int li = 1; li < (int)n->L.size(); ++li)
-        if ((rc = run_layer(n, li, false, st))) return rc;
-    if ((rc = run_head(n, st))) return rc;
+    if (n->use_graph < 0) {
+        const char *g = getenv("AEC_GRAPH");
+        n->use_graph = (g && atoi(g) == 0) ? 0 : 1;
+    }
+    if (n->use_graph && !n->profiling && !n->sg.failed) {
+        aec_net::StepGraph &g = n->sg;
+        if (!g.exec && (rc = build_step_graph(n, ev, off))) {
+            g.failed = true;                  // fall back to plain launches (same kernels, same order)
+            cudaGetLastError();
+        }
+        if (g.exec) {
+            float *out = n->head_cur ? n->head_cur : n->head;
+            if (g.ip.events != ev || g.ip.offsets != off) {
+                g.ip.events = ev; g.ip.offsets = off;
+                cudaKernelNodeParams kp = g.integ_kp;
+                void *args[1] = {&g.ip};
+                kp.kernelParams = args;
+                CU(cudaGraphExecKernelNodeSetParams(g.exec, g.integ, &kp));
+            }
+            if (g.hp.out != out) {
+                g.hp.out = out;
+                cudaKernelNodeParams kp = g.head_kp;
+                void *args[1] = {&g.hp};
+                kp.kernelParams = args;
+                CU(cudaGraphExecKernelNodeSetParams(g.exec, g.head, &kp));
+            }
+            CU(cudaGraphLaunch(g.exec, st));
+            n->launches += g.launches;
+            n->steps++;
+            return AEC_OK;
+        }
+    }
+    if ((rc = step_body(n, ev, off, st))) return rc;
     n->steps++;
     return prof_collect(n, st);
 }

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--kind", default="edge", choices=["edge", "uniform"], help="synthetic stream kind (SURVEY 8d)")
     ap.add_argument("--preroll", type=int, default=48, help="untimed steps to reach the surface's steady state")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-steps", type=int, default=100, help="steps of the single-stream latency measurement (0 = skip)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="extra back-to-back steps after the timed region (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="timed CPU work per core for the baseline")
     ap.add_argument("--cpu-worker", type=int, default=None, help=argparse.SUPPRESS)
@@ -410,6 +411,24 @@ def native_arm(args):
                          "after_seconds": args.sustained_seconds, "steps_run": done,
                          "note": "last 32 of the back-to-back steps (events recycled), rank 0's GPU; power-capped regime"}
 
+    # ---- single-stream latency (the reference's own operating point: batch_size 1, one network object = one stream)
+    latency = None
+    if rank == 0 and args.latency_steps > 0:
+        one = EventNetCuda(H, W, P.EFCN_LAYERS, wts, LEAK, ALPHA, "SAME", n_streams=1, device=local, max_events_per_step=max(2048, B))
+        ev1 = P.synthetic_events(args.kind, 1, args.preroll + args.latency_steps + 1, B, H, W, seed=4242)[0]
+        ev1h = torch.from_numpy(np.ascontiguousarray(ev1)).pin_memory().numpy()
+        off1 = torch.from_numpy(np.array([0, B], np.int32)).pin_memory().numpy()
+        out1 = torch.empty((1,) + one.head_shape, dtype=torch.float32).pin_memory().numpy()
+        for i in range(args.preroll):
+            one.step_packed(ev1h[i], off1, out=out1, cuda_stream=sh)
+        w0 = time.perf_counter()
+        for i in range(args.preroll, args.preroll + args.latency_steps):
+            one.step_packed(ev1h[i], off1, out=out1, cuda_stream=sh)      # blocking: events in, detections out
+        lat = (time.perf_counter() - w0) / args.latency_steps
+        latency = {"ms_per_step": 1e3 * lat, "events_per_s": B / lat, "streams": 1, "steps": args.latency_steps,
+                   "api": "aec_net_step_host, one stream, host events in / host head out per call"}
+        one.close()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -426,6 +445,8 @@ def native_arm(args):
         }
         if sustained is not None:
             line["sustained"] = sustained
+        if latency is not None:
+            line["single_stream"] = latency
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

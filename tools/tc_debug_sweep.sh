@@ -3,7 +3,7 @@
 # (AEC_TC_DEBUG bits; results are invalid, only the timings mean something).
 mkdir -p gpurun_out
 for m in ${MODES:-0 1 3 8 12 9}; do
-  AEC_TC_DEBUG=$m python bench.py --steps 5 --warmup 3 --no-cpu-baseline --sustained-seconds 0 ${BENCH_ARGS} > gpurun_out/dbg_$m.json 2> gpurun_out/dbg_$m.err
+  AEC_TC_DEBUG=$m python bench.py --steps 5 --warmup 3 --no-cpu-baseline --sustained-seconds 0 --latency-steps 0 ${BENCH_ARGS} > gpurun_out/dbg_$m.json 2> gpurun_out/dbg_$m.err
   python - <<PY
 import json
 try:
