@@ -232,7 +232,6 @@ def native_arm(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S, B, K, Wm = args.streams, args.batch, args.steps, max(args.warmup, 3)
     n_e2e = 2 * K + 4
@@ -456,6 +455,12 @@ def native_arm(args):
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON: anything a library prints there (NCCL's version banner under torchrun,
+    # nvcc / loader chatter) goes to stderr instead, and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     args = parse_args()
     if args.cpu_worker is not None:
         cpu_worker(args)
