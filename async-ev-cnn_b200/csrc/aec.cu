@@ -54,6 +54,7 @@ struct HostLayer {
     uint8_t *idx = nullptr, *initIdx = nullptr;
     float *Fp = nullptr, *Ap = nullptr, *initFp = nullptr;   // pool: copy of the conv maps at the argmax
     uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr, *nzr = nullptr;
+    uint32_t *sites = nullptr;      // this layer's work list (region of aec_net::sites)
     float *wgt = nullptr, *bias = nullptr;
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
     bool tc = false;
@@ -76,6 +77,8 @@ struct aec_net {
     int *prev_ts = nullptr;
     uint8_t *active = nullptr, *mask = nullptr;
     uint32_t *sites = nullptr;
+    FrontLayer *front_table = nullptr;   // device copy of the per-layer frontier descriptors (k_frontier_all)
+    int front_max_words = 0;
     int *counts = nullptr, *err_flag = nullptr;
     unsigned long long *accum = nullptr;
     float *head = nullptr;
@@ -444,7 +447,7 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     HostLayer &l = n->L[li];
     const Src src = make_src(n, li - 1);
     tc::TcParams p;
-    p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
+    p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.srcF = src.F; p.a_minus_f = (const char *)src.A - (const char *)src.F; p.zero_f = (const char *)src.F - kMapGuardFloats * 4;
     p.src_stride = src.fstride; p.alpha = src.alpha;
     p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
@@ -466,7 +469,7 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
     HostLayer &l = n->L[li];
     if (l.tc) return run_conv_eval_tc(n, li, st);
     ConvEvalParams p;
-    p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
+    p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.src = make_src(n, li - 1);
     p.wgt = l.wgt; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.Kpad = l.Kpad; p.Npad = l.Npad;
@@ -486,7 +489,7 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     HostLayer &l = n->L[li];
     const HostLayer &c = n->L[li - 1];
     PoolEvalParams p;
-    p.sites = n->sites; p.counter = n->counts + li; p.accum = n->accum + li;
+    p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.F = c.F; p.A = c.A; p.fstride = c.fstride; p.alpha = c.alpha; p.cW = c.W;
     p.idx = l.idx; p.Fp = l.Fp; p.Ap = l.Ap; p.pstride = l.fstride; p.flags = l.flags;
     p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
@@ -506,7 +509,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
         if (with_sweep && (rc = run_sweep(n, li, st))) return rc;
         ConvFrontParams p;
         p.prev_front = pv.front; p.front = l.front; p.signchg = l.signchg; p.nzr = l.nzr; p.prev_nzr = pv.nzr; p.active = n->active;
-        p.sites = n->sites; p.counter = n->counts + li;
+        p.sites = l.sites; p.counter = n->counts + li;
         p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
         p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
         const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4;
@@ -518,7 +521,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     if (with_sweep && (rc = run_sweep(n, li, st))) return rc;     // the (Fp, Ap) copy leaks before it is refreshed
     PoolFrontParams p;
     p.prev_front = pv.front; p.front = l.front; p.flags = l.flags; p.nzr = l.nzr; p.prev_nzr = pv.nzr; p.active = n->active;
-    p.sites = n->sites; p.counter = n->counts + li;
+    p.sites = l.sites; p.counter = n->counts + li;
     p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
     p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
     const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4;
@@ -526,6 +529,22 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     if ((rc = launch_check(n, "k_pool_frontier"))) return rc;
     if ((rc = prof_mark(n, st))) return rc;
     return run_pool_eval(n, li, st);
+}
+
+static int run_eval(aec_net *n, int li, cudaStream_t st)
+{
+    return n->L[li].type == AEC_LAYER_CONV ? run_conv_eval(n, li, st) : run_pool_eval(n, li, st);
+}
+
+static int run_frontier_all(aec_net *n, cudaStream_t st)
+{
+    FrontAllParams p;
+    p.layers = n->front_table; p.n_layers = (int)n->L.size();
+    p.front0 = n->L[0].front; p.nzr0 = n->L[0].nzr; p.words0 = n->L[0].H * n->L[0].Ww;
+    p.max_words = n->front_max_words; p.active = n->active;
+    k_frontier_all<<<n->S, kThreads, (size_t)5 * n->front_max_words * 4, st>>>(p);
+    int rc = launch_check(n, "k_frontier_all");
+    return rc ? rc : prof_mark(n, st);
 }
 
 static HeadParams head_params(aec_net *n, float *out)
@@ -626,7 +645,16 @@ extern "C" int aec_net_finalize(aec_net *n)
         }
         if (l.type != AEC_LAYER_INTEGRATION) maxHW = std::max(maxHW, (size_t)l.H * l.W);
     }
-    if ((rc = dev_alloc(n, &n->sites, S * maxHW, true))) return rc;
+    {
+        size_t total_sites = 0;
+        for (auto &l : n->L)
+            if (l.type != AEC_LAYER_INTEGRATION) total_sites += S * (size_t)l.H * l.W;
+        (void)maxHW;
+        if ((rc = dev_alloc(n, &n->sites, total_sites, true))) return rc;
+        size_t off = 0;
+        for (auto &l : n->L)
+            if (l.type != AEC_LAYER_INTEGRATION) { l.sites = n->sites + off; off += S * (size_t)l.H * l.W; }
+    }
     for (auto &l : n->L)
         if (l.type != AEC_LAYER_INTEGRATION) n->view_elems = std::max(n->view_elems, (size_t)l.H * l.W * l.C);
     if ((rc = dev_alloc(n, &n->view, 4 * n->view_elems, false))) return rc;
@@ -637,6 +665,26 @@ extern "C" int aec_net_finalize(aec_net *n)
     const HostLayer &last = n->L.back();
     n->head_per_stream = (size_t)last.H * last.W * last.C;
     if ((rc = dev_alloc(n, &n->head, S * n->head_per_stream, true))) return rc;
+
+    // frontier table of the fused all-layer frontier kernel
+    {
+        std::vector<FrontLayer> tab(n->L.size());
+        memset(tab.data(), 0, tab.size() * sizeof(FrontLayer));
+        int mw = n->L[0].H * n->L[0].Ww;
+        for (size_t li = 1; li < n->L.size(); ++li) {
+            const HostLayer &l = n->L[li], &pv = n->L[li - 1];
+            FrontLayer &f = tab[li];
+            f.type = l.type; f.Hin = pv.H; f.Win = pv.W; f.WwIn = pv.Ww; f.H = l.H; f.W = l.W; f.Ww = l.Ww;
+            f.kh = l.kh; f.kw = l.kw; f.pad_t = l.pad_t; f.pad_l = l.pad_l; f.stride = l.stride;
+            f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.sites = l.sites; f.counter = n->counts + li;
+            mw = std::max(mw, std::max(pv.H * pv.Ww, std::max(pv.H * l.Ww, l.H * l.Ww)));
+        }
+        n->front_max_words = mw;
+        if ((size_t)5 * mw * 4 > 200 * 1024) return fail(AEC_EINVAL, "frame too large for the frontier kernel's shared memory");
+        if ((rc = dev_alloc(n, &n->front_table, tab.size(), false))) return rc;
+        CU(cudaMemcpy(n->front_table, tab.data(), tab.size() * sizeof(FrontLayer), cudaMemcpyHostToDevice));
+        CU(cudaFuncSetAttribute(k_frontier_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)5 * mw * 4, 48 * 1024)));
+    }
 
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
@@ -708,7 +756,7 @@ extern "C" int aec_net_finalize(aec_net *n)
     for (size_t li = 1; li < n->L.size(); ++li) {
         HostLayer &l = n->L[li];
         const int HW = l.H * l.W;
-        k_all_sites<<<(HW + kThreads - 1) / kThreads, kThreads, 0, st>>>(n->sites, n->counts + li, HW);
+        k_all_sites<<<(HW + kThreads - 1) / kThreads, kThreads, 0, st>>>(l.sites, n->counts + li, HW);
         if ((rc = launch_check(n, "k_all_sites"))) return rc;
         if (l.type == AEC_LAYER_CONV) {
             if ((rc = run_conv_eval(n, (int)li, st))) return rc;
@@ -794,8 +842,9 @@ static int step_body(aec_net *n, const int32_t *ev, const int32_t *off, cudaStre
     int rc;
     if ((rc = run_integrate(n, ev, off, st))) return rc;
     if ((rc = run_sweep(n, -1, st))) return rc;
+    if ((rc = run_frontier_all(n, st))) return rc;
     for (int li = 1; li < (int)n->L.size(); ++li)
-        if ((rc = run_layer(n, li, false, st))) return rc;
+        if ((rc = run_eval(n, li, st))) return rc;
     return run_head(n, st);
 }
 

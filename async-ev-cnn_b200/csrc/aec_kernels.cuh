@@ -625,6 +625,149 @@ __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3+K4 fused: the frontier of EVERY layer in one launch, one CTA per stream.  Frontiers, sticky flags and
+// non-zero-rate bits are pure bitmap logic on the previous layer's bitmaps (the sign flips come from the leak
+// sweep, the flags from earlier steps), so the whole chain can run before any evaluation: the previous
+// layer's two bitmaps stay in shared memory from layer to layer, and a step issues one frontier launch
+// instead of one per layer.  Each layer has its own work list (the evaluations run afterwards, back to back).
+// Same arithmetic as k_conv_frontier / k_pool_frontier (kept for the layer-at-a-time interface).
+// Dynamic shared memory: 5 * max_words * 4 bytes (max_words = largest H*Ww of any layer, incl. H_in*Ww mixes).
+// ---------------------------------------------------------------------------------------------
+struct FrontLayer {
+    int type;                     // 1 conv, 2 pool (AEC_LAYER_*)
+    int Hin, Win, WwIn, H, W, Ww;
+    int kh, kw, pad_t, pad_l, stride;
+    uint32_t *front, *signchg, *flags, *nzr;
+    uint32_t *sites;
+    int *counter;
+};
+struct FrontAllParams {
+    const FrontLayer *layers;     // [n_layers], entry 0 unused (integration layer)
+    int n_layers;
+    const uint32_t *front0, *nzr0;   // layer 0 bitmaps written by k_integrate, [S][H0*Ww0]
+    int words0;
+    int max_words;
+    const uint8_t *active;
+};
+
+__global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);        // previous layer's frontier
+    uint32_t *bufB = bufA + p.max_words;                            // previous layer's non-zero-rate bits
+    uint32_t *Hd = bufB + p.max_words;                              // scratch (horizontal dilation)
+    uint32_t *N = Hd + p.max_words;                                 // this layer's work set
+    uint32_t *Z = N + p.max_words;                                  // this layer's non-zero-rate bits
+    __shared__ int scratch[9];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (!p.active[s]) {
+        for (int li = 1; li < p.n_layers; ++li) {
+            const FrontLayer &L = p.layers[li];
+            uint32_t *front = L.front + (long long)s * L.H * L.Ww;
+            for (int i = tid; i < L.H * L.Ww; i += kThreads) front[i] = 0u;
+        }
+        return;
+    }
+    for (int i = tid; i < p.words0; i += kThreads) {
+        bufA[i] = p.front0[(long long)s * p.words0 + i];
+        bufB[i] = p.nzr0[(long long)s * p.words0 + i];
+    }
+    __syncthreads();
+    for (int li = 1; li < p.n_layers; ++li) {
+        const FrontLayer L = p.layers[li];
+        const int nout = L.H * L.Ww;
+        const uint32_t lastmask = (L.W & 31) ? ((1u << (L.W & 31)) - 1u) : 0xffffffffu;
+        uint32_t *front = L.front + (long long)s * nout;
+        uint32_t *nz = L.nzr + (long long)s * nout;
+        if (L.type == 1) {
+            auto hdilate = [&](const uint32_t *P) {
+                for (int i = tid; i < L.Hin * L.Ww; i += kThreads) {
+                    const int y = i / L.Ww, w = i - y * L.Ww;
+                    uint32_t acc = 0u;
+                    for (int d = L.pad_l - L.kw + 1; d <= L.pad_l; ++d) acc |= row_shift(P + y * L.WwIn, L.WwIn, w, d);
+                    if (w == L.Ww - 1) acc &= lastmask;
+                    Hd[i] = acc;
+                }
+            };
+            auto vdilate = [&](int i) {
+                const int y = i / L.Ww, w = i - y * L.Ww;
+                uint32_t acc = 0u;
+                for (int d = L.pad_t - L.kh + 1; d <= L.pad_t; ++d) {
+                    const int yi = y - d;
+                    if (yi >= 0 && yi < L.Hin) acc |= Hd[yi * L.Ww + w];
+                }
+                return acc;
+            };
+            hdilate(bufA);
+            __syncthreads();
+            uint32_t *sc = L.signchg + (long long)s * nout;
+            for (int i = tid; i < nout; i += kThreads) N[i] = vdilate(i);
+            __syncthreads();
+            hdilate(bufB);
+            __syncthreads();
+            for (int i = tid; i < nout; i += kThreads) {
+                const uint32_t n = N[i];
+                const uint32_t flips = sc[i];
+                if (flips) sc[i] = 0u;
+                const uint32_t f = n | flips;
+                front[i] = f;
+                uint32_t z = nz[i];
+                if (n) { z = (z & ~n) | (n & vdilate(i)); nz[i] = z; }
+                Z[i] = z;
+                bufA[i] = f;          // safe: bufA was last read by the first hdilate, two barriers ago
+            }
+            __syncthreads();
+        } else {
+            uint32_t *fl = L.flags + (long long)s * nout;
+            auto window_or = [&](const uint32_t *P, int i) {
+                const int oy = i / L.Ww, w = i - oy * L.Ww;
+                uint32_t hit = 0u;
+                if (L.kh == 2 && L.kw == 2 && L.stride == 2) {
+                    const uint32_t *r0 = P + (2 * oy) * L.WwIn, *r1 = r0 + L.WwIn;
+                    uint32_t lo = (2 * w < L.WwIn) ? (r0[2 * w] | r1[2 * w]) : 0u;
+                    uint32_t hi = (2 * w + 1 < L.WwIn) ? (r0[2 * w + 1] | r1[2 * w + 1]) : 0u;
+                    lo |= lo >> 1;
+                    hi |= hi >> 1;
+                    hit = compress_even_bits(lo) | (compress_even_bits(hi) << 16);
+                } else {
+                    for (int b = 0; b < 32; ++b) {
+                        const int ox = w * 32 + b;
+                        if (ox >= L.W) break;
+                        bool any = false;
+                        for (int dy = 0; dy < L.kh && !any; ++dy)
+                            for (int dx = 0; dx < L.kw; ++dx) {
+                                const int iy = oy * L.stride + dy, ix = ox * L.stride + dx;
+                                if ((P[iy * L.WwIn + (ix >> 5)] >> (ix & 31)) & 1u) { any = true; break; }
+                            }
+                        if (any) hit |= 1u << b;
+                    }
+                }
+                if (w == L.Ww - 1) hit &= lastmask;
+                return hit;
+            };
+            for (int i = tid; i < nout; i += kThreads) {
+                const uint32_t hit = window_or(bufA, i);
+                const uint32_t f = fl[i] & ~hit;      // maxpool.py:118-120
+                const uint32_t wset = hit | f;        // maxpool.py:123-126
+                fl[i] = f;
+                N[i] = wset;
+                front[i] = wset;
+                uint32_t z = nz[i];
+                if (wset) { z = (z & ~wset) | (wset & window_or(bufB, i)); nz[i] = z; }
+                Z[i] = z;
+            }
+            __syncthreads();
+            for (int i = tid; i < nout; i += kThreads) bufA[i] = N[i];
+            __syncthreads();
+        }
+        emit_sites(N, L.H, L.W, L.Ww, (uint32_t)s * (uint32_t)(L.H * L.W), L.sites, L.counter, scratch);
+        __syncthreads();
+        for (int i = tid; i < nout; i += kThreads) bufB[i] = Z[i];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5: pool evaluation over the work list.   maxpool.py:130-151, cutils.pyx:161-177
 //   per (window, channel): argmax of F over the window rows (ascending ky*kw+kx), ties -> smaller
 //   rate R = A*slope(F), then smaller row; argmin of R (first); unstable = R[argmax] != R[argmin];

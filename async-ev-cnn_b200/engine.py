@@ -263,10 +263,7 @@ class EventNetCuda:
     # -- measurement ---------------------------------------------------------------------------
     def slot_names(self):
         """Names of the launches of one step, in order (matches aec_net_read_profile slots)."""
-        names = ["surface", "leak_sweep"]
-        for nm in self.names[1:]:
-            names += [nm + ".frontier", nm + ".eval"]
-        return names + ["head"]
+        return ["surface", "leak_sweep", "all.frontier"] + [nm + ".eval" for nm in self.names[1:]] + ["head"]
 
     def profile(self, enable=True):
         N.check(self._lib.aec_net_profile(self._h, 1 if enable else 0))
