@@ -468,6 +468,17 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
 {
     HostLayer &l = n->L[li];
     if (l.tc) return run_conv_eval_tc(n, li, st);
+    static const bool no_stencil = getenv("AEC_CONV_PATH") && strcmp(getenv("AEC_CONV_PATH"), "simt") == 0;
+    if (n->L[li - 1].type == AEC_LAYER_INTEGRATION && l.C % 4 == 0 && l.C <= kStencilMaxC && l.kh * l.kw <= kStencilMaxK && !no_stencil) {
+        StencilParams p;
+        p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
+        p.S = n->surface; p.sstride = (long long)n->L[0].H * n->L[0].W; p.Hin = n->L[0].H; p.Win = n->L[0].W;
+        p.wgt = l.wgt; p.bias = l.bias; p.Npad = l.Npad; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
+        p.C = l.C; p.H = l.H; p.W = l.W; p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+        k_conv_stencil<<<n->num_sms * 8, kThreads, 0, st>>>(p);
+        int rc = launch_check(n, "k_conv_stencil");
+        return rc ? rc : prof_mark(n, st);
+    }
     ConvEvalParams p;
     p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.src = make_src(n, li - 1);

@@ -1037,6 +1037,73 @@ __global__ void __launch_bounds__(kThreads) k_conv_eval(ConvEvalParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6b: re-evaluation of a conv layer that reads the integration surface directly (Cin = 1): a kh x kw stencil,
+// not a GEMM.   conv2d.py:118-123 with V = (float)S, R = [S > 0] (integration.py:33-43)
+//   thread = (site, 4 output channels); the kh*kw surface values are read once per thread (float64 -> V, R),
+//   weights [k][Cout] sit in shared memory; each output is accumulated sequentially over k in one thread
+//   (position-independent summation order, like the GEMM kernels).
+// ---------------------------------------------------------------------------------------------
+struct StencilParams {
+    const uint32_t *sites;
+    const int *counter;
+    unsigned long long *accum;
+    const double *S;       // [streams][Hin*Win]
+    long long sstride;
+    int Hin, Win;
+    const float *wgt;      // [Kpad][Npad]
+    const float *bias;
+    int Npad;
+    float *F, *A;
+    long long fstride;
+    int C, H, W;           // output (C % 4 == 0)
+    int kh, kw, pad_t, pad_l;
+};
+constexpr int kStencilMaxK = 64, kStencilMaxC = 64;
+
+__global__ void __launch_bounds__(kThreads) k_conv_stencil(StencilParams p)
+{
+    __shared__ __align__(16) float w_s[kStencilMaxK * kStencilMaxC];
+    __shared__ __align__(16) float b_s[kStencilMaxC];
+    const int K = p.kh * p.kw;
+    for (int i = threadIdx.x; i < K * p.C; i += kThreads) w_s[i] = p.wgt[(i / p.C) * p.Npad + (i % p.C)];
+    for (int i = threadIdx.x; i < p.C; i += kThreads) b_s[i] = p.bias[i];
+    __syncthreads();
+    const int n = *p.counter;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.accum, (unsigned long long)n);
+    const int CG = p.C >> 2;
+    const long long total = (long long)n * CG;
+    const int HW = p.H * p.W;
+    for (long long wi = (long long)blockIdx.x * kThreads + threadIdx.x; wi < total; wi += (long long)gridDim.x * kThreads) {
+        const uint32_t e = p.sites[wi / CG];
+        const int c = (int)(wi % CG) * 4;
+        const int s = (int)(e / (uint32_t)HW);
+        const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
+        const int y = site / p.W, x = site - y * p.W;
+        const double *Sb = p.S + (long long)s * p.sstride;
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f), a = f;
+        int k = 0;
+        for (int ky = 0; ky < p.kh; ++ky)
+            for (int kx = 0; kx < p.kw; ++kx, ++k) {
+                const int iy = y + ky - p.pad_t, ix = x + kx - p.pad_l;
+                float v = 0.f, r = 0.f;
+                if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) {
+                    const double sv = Sb[(long long)iy * p.Win + ix];
+                    v = __double2float_rn(sv);
+                    r = sv > 0.0 ? 1.f : 0.f;
+                }
+                const float4 w = *reinterpret_cast<const float4 *>(&w_s[k * p.C + c]);
+                f.x = fmaf(v, w.x, f.x); f.y = fmaf(v, w.y, f.y); f.z = fmaf(v, w.z, f.z); f.w = fmaf(v, w.w, f.w);
+                a.x = fmaf(r, w.x, a.x); a.y = fmaf(r, w.y, a.y); a.z = fmaf(r, w.z, a.z); a.w = fmaf(r, w.w, a.w);
+            }
+        const float4 b = *reinterpret_cast<const float4 *>(&b_s[c]);
+        f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+        const long long o = (long long)s * p.fstride + (long long)site * p.C + c;
+        *reinterpret_cast<float4 *>(p.F + o) = f;
+        *reinterpret_cast<float4 *>(p.A + o) = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K7: head = featuremap() of the last layer, channel-last (event_numpy.py:79,101).
 // ---------------------------------------------------------------------------------------------
 struct HeadParams {
