@@ -903,7 +903,7 @@ extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t 
         const char *g = getenv("AEC_GRAPH");
         n->use_graph = (g && atoi(g) == 0) ? 0 : 1;
     }
-    if (n->use_graph && !n->profiling && !n->sg.failed) {
+    if (n->use_graph && !n->profiling && !n->tc_timing_on && !n->sg.failed) {
         aec_net::StepGraph &g = n->sg;
         if (!g.exec && (rc = build_step_graph(n, ev, off))) {
             g.failed = true;                  // fall back to plain launches (same kernels, same order)

@@ -308,7 +308,7 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ __align__(8) uint64_t bar_x_full[kSiteStages][2], bar_x_empty[kSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
+    __shared__ __align__(8) uint64_t bar_x_full[kSiteStages], bar_x_empty[kSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[kSiteRing], bar_si_free[kSiteRing];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) SiteSrc s_src[kSiteRing][kUnitSites];
@@ -329,8 +329,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
 
     if (tid == 0) {
         for (int i = 0; i < kSiteStages; ++i) {
-            mbar_init(smem_u32(&bar_x_full[i][0]), kGroupThreads);
-            mbar_init(smem_u32(&bar_x_full[i][1]), kGroupThreads);
+            mbar_init(smem_u32(&bar_x_full[i]), 2 * kGroupThreads);      // both halves of the stage (two producer groups)
             mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
         for (int i = 0; i < p.w_stages; ++i) {
@@ -500,11 +499,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
                 const uint32_t sx = qx % (uint32_t)kSiteStages;
                 const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
-                timed_wait(smem_u32(&bar_x_full[sx][0]), px, timing, tw_x);
-                timed_wait(smem_u32(&bar_x_full[sx][1]), px, timing, tw_x);
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
+                    // every wait costs ~170 cycles even when the barrier is already complete: the weights (normally early)
+                    // first, the site stage (normally the last thing to arrive) last, one barrier for both of its halves
                     timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                    if (mt == 0) timed_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
                     asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qw & 3u)) : "memory");
                 }
             }
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes + (uint32_t)c.h * (uint32_t)kItemTileBytes;
             item_store(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
             fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
-            mbar_arrive(smem_u32(&bar_x_full[sx][c.h]));
+            mbar_arrive(smem_u32(&bar_x_full[sx]));
         };
         Pos cur;
         cur.q = (uint32_t)g; cur.ul = 0; cur.kb = g >> 1; cur.h = g & 1;
