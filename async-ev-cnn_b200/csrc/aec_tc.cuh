@@ -10,12 +10,16 @@
 //                                              N = 256 = 128 sites x {value row, rate row}
 //                                              K = kh*kw*Cin ordered (ky,kx,ci), blocks of 32
 // (conv2d.py:118-123: the value map and the rate map use the same gather addresses and the same
-// weights).  Measured on the previous orientation (sites as M, N = Cout <= 128): the single MMA-issuing
-// thread spends ~115 cycles per tcgen05.mma in uniform-datapath bookkeeping, more than the 16-64
-// cycle tensor floor of such small instructions, so the kernel was issue-bound (AEC_TC_DEBUG
-// ablations, profiles/r1b_summary.md).  With N = 256 every instruction carries 128 cycles of tensor
-// work and the accumulator comes out channel-per-lane, so the epilogue writes 32 consecutive
-// channels of one site per warp store (one 128-byte line) instead of 32 scattered 16-byte pieces.
+// weights).  Measured (tools/bench_umma.cu): a tcgen05.mma with M = 128 takes max(64, N/2) cycles, so
+// N = 256 instructions carry twice the work of the N <= 128 ones of the sites-as-M orientation at the
+// same issue cost, the accumulator comes out channel-per-lane - the epilogue writes 32 consecutive channels
+// of one site per warp store (one 128-byte line) - and two weight tiles can share one gather (Cout >= 256).
+// A layer with 32 output channels repeats them 4x along M (the rows are free: M is 128 anyway) so that
+// all four epilogue warps share its 256 columns.
+//
+// What bounds it (profiles/r1c_summary.md, r1d_summary.md): per K block the tensor core reads 12 x 12 KB
+// of operands, the producers store a 64 KB site stage and the loader 32 KB of weights - 240 KB per 1536
+// cycles, the measured shared-memory ceiling (~94 B/cycle of MMA reads + ~64 B/cycle of stores).
 //
 // Precision: north_star asks for float32 maps within 1e-4 relative, and the oracle's pool ties must
 // stay exact, so a bare TF32 product (10-bit mantissa) is not enough.  Every operand is split into
@@ -29,9 +33,10 @@
 //   warp  4     MMA issuer: a converged warp, one elected lane issues tcgen05.mma and the commits
 //   warp  7     gatekeeper: does every mbarrier wait on the MMA warp's behalf (named-barrier hand-off)
 //   warp  5     weight loader (one lane): cp.async.bulk of the pre-split, pre-swizzled weight image
-//   warp  6     site decoder: work-list entries -> (stream, y, x, output offset), double buffered
+//   warp  6     site decoder: work-list entries -> source pointer, in-map tap bits, output offset (ring of 4 units)
 //   warps 8-19  gather producers, 3 groups of 4 warps taking (K block, half) items round-robin:
-//               global -> registers (V = F*slope, R = A*slope) -> hi/lo split -> swizzled smem
+//               global -> registers (V = F*slope, R = A*slope) -> hi/lo split -> swizzled smem;
+//               the next item's loads are issued before the current one is converted (setmaxnreg: 112 regs)
 // Pipelines (all mbarrier based): site stages (producers <-> MMA), weight stages (loader <-> MMA),
 // accumulator buffers (MMA <-> epilogue), site-info buffers (decoder <-> producers/epilogue).
 #pragma once
