@@ -245,3 +245,29 @@ def test_ndata_decode_kernel_equals_oracle():
                 assert np.array_equal(pols[r], np.asarray(p, np.int32).reshape(-1))
     with pytest.raises(ValueError):
         decode_ndata([np.zeros(7, np.uint8)])
+
+
+@pytest.mark.parametrize("layers,h,w", [
+    ("conv1=3,3,1,4 conv2=7,7,4,8 pool1=2,2 conv3=1,1,8,4", 28, 36),        # 49 taps: the SIMT GEMM fallback (tap bitmask is 32 wide)
+    ("conv1=3,3,1,8 pool1=3,3 conv2=3,3,8,12 pool2=3,3 conv3=3,3,12,4", 36, 54),   # 3x3 / stride-3 pools: generic window path
+    ("conv1=3,3,1,6 conv2=3,3,6,10 pool1=2,2 conv3=3,3,10,7", 24, 40),       # channel counts that are not multiples of 4
+])
+def test_unusual_shapes_against_live_oracle_exact(layers, h, w):
+    S, steps = 3, 40
+    wts = P.xavier_weights(layers, seed=13, exact=True)
+    evs = P.synthetic_events("uniform", S, steps, 20, h, w, seed=17, dt_int=(1, 5))
+    net = EventNetCuda(h, w, layers, wts, 1.0 / 64, 0.5, "SAME", n_streams=S)
+    oracles = [OracleEventNet(h, w, layers, wts, 1.0 / 64, 0.5, "SAME") for _ in range(S)]
+    for t in range(steps):
+        heads = net.step([evs[s, t] for s in range(S)])
+        for s in range(S):
+            assert np.array_equal(heads[s], oracles[s].step(evs[s, t])), "step %d stream %d head" % (t, s)
+        if t % 8 == 7:
+            for s in range(S):
+                oa = OracleAdapter(oracles[s])
+                for i in range(len(net.names)):
+                    so, sc = oa.state(i), net.state(i, s)
+                    for key in so:
+                        assert np.array_equal(sc[key], so[key]), "step %d stream %d layer %s %s" % (t, s, net.names[i], key)
+                    assert np.array_equal(net.frontier(i, s), oa.frontier(i))
+    net.close()
