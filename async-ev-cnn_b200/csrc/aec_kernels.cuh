@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
     const int32_t *ev = p.events + (long long)e0 * 3;
 
     for (int i = tid; i < p.hash_slots; i += kThreads) { hkey[i] = -1; hval[i] = -1; }
-    for (int i = tid; i < nbm; i += kThreads) { bm[i] = 0u; al[i] = 0u; }
+    uint32_t *alive = p.alive + (long long)s * nbm;
+    for (int i = tid; i < nbm; i += kThreads) { bm[i] = 0u; al[i] = alive[i]; }
 
     // t_L = max(ts)
     int tmax = INT_MIN;
@@ -266,17 +267,39 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
         }
     }
 
-    // dense leak + clamp (integration.py:63-68)
+    // leak + clamp (integration.py:63-68).  A pixel with S == 0 stays 0 and emits nothing, so only the pixels
+    // alive after the previous step are touched: `al` starts as the previous alive bitmap and is walked one
+    // word per warp, lane b owning bit b (coalesced over the set bits; the surface is mostly dead, so this
+    // reads a fraction of it), four words in flight per warp.
     double *surf = p.surface + (long long)s * HW;
-    for (int i = tid; i < HW; i += kThreads) {
-        const double v = surf[i];
-        const double w = __dsub_rn(v, delta);
-        const bool dead = w <= 0.0;
-        const double nv = dead ? 0.0 : w;
-        if (nv != v) surf[i] = nv;
-        if (v > 0.0) {                 // alive before: died now (output event) or still alive
-            const int y = i / p.W, x = i - y * p.W;
-            atomicOr(&(dead ? bm : al)[y * p.Ww + (x >> 5)], 1u << (x & 31));
+    const int lane = tid & 31, wid = tid >> 5;
+    constexpr int kWarps = kThreads / 32, kU = 4;
+    for (int w0 = wid; w0 < nbm; w0 += kWarps * kU) {
+        uint32_t bits[kU];
+        double v[kU];
+        int pix[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int wi = w0 + u * kWarps;
+            bits[u] = wi < nbm ? al[wi] : 0u;
+            const int y = wi / p.Ww;
+            pix[u] = y * p.W + (wi - y * p.Ww) * 32 + lane;
+            v[u] = 0.0;
+            if ((bits[u] >> lane) & 1u) v[u] = surf[pix[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (bits[u] == 0u) continue;                       // warp-uniform
+            const bool mine = (bits[u] >> lane) & 1u;
+            const double w = __dsub_rn(v[u], delta);
+            const bool dead = mine && w <= 0.0;
+            if (mine) surf[pix[u]] = dead ? 0.0 : w;
+            const uint32_t died = __ballot_sync(0xffffffffu, dead);
+            if (lane == 0) {
+                const int wi = w0 + u * kWarps;
+                al[wi] = bits[u] & ~died;                       // still alive
+                bm[wi] = died;                                  // died now: an output event
+            }
         }
     }
     __syncthreads();
@@ -299,7 +322,6 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
         else atomicAnd(&al[y * p.Ww + (x >> 5)], ~(1u << (x & 31)));
     }
     __syncthreads();
-    uint32_t *alive = p.alive + (long long)s * nbm;
     for (int i = tid; i < nbm; i += kThreads) { front[i] = bm[i]; alive[i] = al[i]; }
     if (tid == 0) { p.active[s] = 1; p.delta[s] = delta; p.prev_ts[s] = t_last; }
 }
