@@ -271,3 +271,107 @@ def test_unusual_shapes_against_live_oracle_exact(layers, h, w):
                         assert np.array_equal(sc[key], so[key]), "step %d stream %d layer %s %s" % (t, s, net.names[i], key)
                     assert np.array_equal(net.frontier(i, s), oa.frontier(i))
     net.close()
+
+
+def test_long_run_through_pixel_deaths_exact():
+    """300 steps with a leak that kills a pixel within a few steps: the surface kernel walks only the pixels alive
+    after the previous step (its alive bitmap), so births, deaths and re-births must keep that bitmap exact."""
+    layers, h, w, S, steps, batch = SMALL, 32, 64, 3, 300, 12
+    wts = P.xavier_weights(layers, seed=2, exact=True)
+    evs = P.synthetic_events("edge", S, steps, batch, h, w, seed=31, dt_int=(1, 9))
+    net = EventNetCuda(h, w, layers, wts, 1.0 / 128, 0.25, "SAME", n_streams=S)
+    oracles = [OracleEventNet(h, w, layers, wts, 1.0 / 128, 0.25, "SAME") for _ in range(S)]
+    deaths, alive_before = 0, [None] * S
+    for t in range(steps):
+        per = [evs[s, t] if (s * 7 + t) % 11 else None for s in range(S)]
+        heads = net.step(per)
+        for s in range(S):
+            if per[s] is None:
+                continue
+            ho = oracles[s].step(per[s])
+            assert np.array_equal(heads[s], ho), "step %d stream %d head" % (t, s)
+        if t % 25 == 24:
+            for s in range(S):
+                surf_o = OracleAdapter(oracles[s]).state(0)["S"]
+                assert np.array_equal(net.state(0, s)["S"], surf_o), "step %d stream %d surface" % (t, s)
+                alive = np.asarray(surf_o) > 0
+                if alive_before[s] is not None:
+                    deaths += int((alive_before[s] & ~alive).sum())
+                alive_before[s] = alive
+    assert deaths > 0, "the test is meant to run through pixel deaths"
+    for s in range(S):
+        oa = OracleAdapter(oracles[s])
+        for i in range(len(net.names)):
+            so, sc = oa.state(i), net.state(i, s)
+            for key in so:
+                assert np.array_equal(sc[key], so[key]), "final state stream %d layer %s %s" % (s, net.names[i], key)
+    net.close()
+
+
+def test_duplicate_pixels_and_event_count_boundary_exact():
+    """All events of a step on one pixel (last duplicate wins, integration.py:71-80), a step of exactly
+    max_events_per_step events, and one more than that (rejected, state untouched)."""
+    layers, h, w = SMALL, 32, 48
+    wts = P.xavier_weights(layers, seed=4, exact=True)
+    cap = 64
+    net = EventNetCuda(h, w, layers, wts, 1.0 / 64, 0.5, "SAME", n_streams=2, max_events_per_step=cap)
+    orc = OracleEventNet(h, w, layers, wts, 1.0 / 64, 0.5, "SAME")
+    rng = np.random.default_rng(0)
+    ts = 0
+
+    def batch(n, same_pixel):
+        nonlocal ts
+        t = ts + np.cumsum(rng.integers(1, 4, size=n))
+        ts = int(t[-1])
+        if same_pixel:
+            y = np.full(n, 7); x = np.full(n, 9)
+        else:
+            y = rng.integers(0, h, size=n); x = rng.integers(0, w, size=n)
+        return np.stack([y, x, t], axis=1).astype(np.int32)
+
+    for n, same in [(cap, True), (cap, False), (1, False), (cap, True), (5, False)]:
+        ev = batch(n, same)
+        heads = net.step([ev, ev])
+        ho = orc.step(ev)
+        assert np.array_equal(heads[0], ho) and np.array_equal(heads[1], ho)
+    oa = OracleAdapter(orc)
+    for i in range(len(net.names)):
+        so, sc = oa.state(i), net.state(i, 1)
+        for key in so:
+            assert np.array_equal(sc[key], so[key]), "layer %s %s" % (net.names[i], key)
+    with pytest.raises(IndexError):
+        net.step([batch(cap + 1, False), None])
+    ev = batch(3, False)                                   # the rejected call left no trace
+    heads = net.step([ev, ev])
+    assert np.array_equal(heads[1], orc.step(ev))
+    net.close()
+
+
+def test_diagnostics_api_is_consistent_with_the_maps():
+    """aec_net_sweep_stats / aec_net_tc_timing: the live-site bitmap must cover every element with a non-zero rate
+    (it decides what the leak sweep touches), and the role timers must tick on the tensor-core layers."""
+    g = Golden(golden_path("efcn_edge"))
+    net = EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=2)
+    ad = CudaAdapter(net, stream=1)
+    for s in range(6):
+        ad.step(g.events(s))
+    st = net.sweep_stats()
+    nz = tot = 0
+    for i, nm in enumerate(net.names):
+        if "conv" in nm:
+            for s in range(2):
+                a = net.state(i, s)["A"]
+                nz += int(np.count_nonzero(a)); tot += a.size
+    assert st["conv_elems"] == tot
+    assert nz <= st["live_conv_elems"] <= tot
+    assert 0 < st["nz_groups"] <= st["groups"]
+    assert len(net.tc_layers()) >= 5
+    net.tc_timing(True)
+    ad.step(g.events(6))
+    tm = net.read_tc_timing()
+    net.tc_timing(False)
+    assert tm, "no tensor-core layer reported timing"
+    for nm, d in tm.items():
+        assert d["ctas"] > 0 and d["mma_total"] > 0 and d["prod_total"] > 0 and d["epi_total"] > 0, (nm, d)
+    assert np.array_equal(ad.step(g.events(7)).shape, g.z["heads"][7].shape)
+    net.close()
