@@ -504,8 +504,9 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     p.F = c.F; p.A = c.A; p.fstride = c.fstride; p.alpha = c.alpha; p.cW = c.W;
     p.idx = l.idx; p.Fp = l.Fp; p.Ap = l.Ap; p.pstride = l.fstride; p.flags = l.flags;
     p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
-    if (l.C % 4 == 0) k_pool_eval<4><<<n->num_sms * 8, kThreads, 0, st>>>(p);
-    else k_pool_eval<1><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    if (l.C % 4 == 0 && l.kh == 2 && l.kw == 2 && l.stride == 2) k_pool_eval<4, true><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    else if (l.C % 4 == 0) k_pool_eval<4, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    else k_pool_eval<1, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
     int rc = launch_check(n, "k_pool_eval");
     return rc ? rc : prof_mark(n, st);
 }

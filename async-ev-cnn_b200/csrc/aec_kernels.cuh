@@ -844,7 +844,9 @@ __device__ __forceinline__ void pool_next(PoolBest &b, int row, float f, float a
     if (r < b.rlow) b.rlow = r;                                                          // cutils.pyx:173-174
 }
 
-template <int VEC>
+// WIN2: the 2x2 / stride-2 window of every EFCN pool layer, with the eight 16-byte loads of an item issued before
+// the first compare (the generic loop has run-time bounds and makes four dependent round trips to memory).
+template <int VEC, bool WIN2>
 __global__ void __launch_bounds__(kThreads) k_pool_eval(PoolEvalParams p)
 {
     const int n = *p.counter;
@@ -861,26 +863,43 @@ __global__ void __launch_bounds__(kThreads) k_pool_eval(PoolEvalParams p)
         const float *Fb = p.F + (long long)s * p.fstride;
         const float *Ab = p.A + (long long)s * p.fstride;
         PoolBest best[VEC];
-        int row = 0;
-        for (int dy = 0; dy < p.kh; ++dy)
-            for (int dx = 0; dx < p.kw; ++dx, ++row) {
-                const long long off = ((long long)(oy * p.stride + dy) * p.cW + (ox * p.stride + dx)) * p.C + c;
-                float f[VEC], a[VEC];
-                if constexpr (VEC == 4) {
-                    const float4 f4 = __ldg(reinterpret_cast<const float4 *>(Fb + off));
-                    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(Ab + off));
-                    f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
-                    a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-                } else {
-                    f[0] = Fb[off];
-                    a[0] = Ab[off];
-                }
+        if constexpr (WIN2 && VEC == 4) {
+            const long long o00 = ((long long)(oy * 2) * p.cW + ox * 2) * p.C + c;
+            const long long o10 = o00 + (long long)p.cW * p.C;
+            const float4 f0 = __ldg(reinterpret_cast<const float4 *>(Fb + o00)), a0 = __ldg(reinterpret_cast<const float4 *>(Ab + o00));
+            const float4 f1 = __ldg(reinterpret_cast<const float4 *>(Fb + o00 + p.C)), a1 = __ldg(reinterpret_cast<const float4 *>(Ab + o00 + p.C));
+            const float4 f2 = __ldg(reinterpret_cast<const float4 *>(Fb + o10)), a2 = __ldg(reinterpret_cast<const float4 *>(Ab + o10));
+            const float4 f3 = __ldg(reinterpret_cast<const float4 *>(Fb + o10 + p.C)), a3 = __ldg(reinterpret_cast<const float4 *>(Ab + o10 + p.C));
+            const float fr[4][4] = {{f0.x, f0.y, f0.z, f0.w}, {f1.x, f1.y, f1.z, f1.w}, {f2.x, f2.y, f2.z, f2.w}, {f3.x, f3.y, f3.z, f3.w}};
+            const float ar[4][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w}, {a3.x, a3.y, a3.z, a3.w}};
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    if (row == 0) pool_first(best[v], f[v], a[v], p.alpha);
-                    else pool_next(best[v], row, f[v], a[v], p.alpha);
-                }
+            for (int v = 0; v < 4; ++v) {
+                pool_first(best[v], fr[0][v], ar[0][v], p.alpha);
+#pragma unroll
+                for (int row = 1; row < 4; ++row) pool_next(best[v], row, fr[row][v], ar[row][v], p.alpha);
             }
+        } else {
+            int row = 0;
+            for (int dy = 0; dy < p.kh; ++dy)
+                for (int dx = 0; dx < p.kw; ++dx, ++row) {
+                    const long long off = ((long long)(oy * p.stride + dy) * p.cW + (ox * p.stride + dx)) * p.C + c;
+                    float f[VEC], a[VEC];
+                    if constexpr (VEC == 4) {
+                        const float4 f4 = __ldg(reinterpret_cast<const float4 *>(Fb + off));
+                        const float4 a4 = __ldg(reinterpret_cast<const float4 *>(Ab + off));
+                        f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
+                        a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+                    } else {
+                        f[0] = Fb[off];
+                        a[0] = Ab[off];
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        if (row == 0) pool_first(best[v], f[v], a[v], p.alpha);
+                        else pool_next(best[v], row, f[v], a[v], p.alpha);
+                    }
+                }
+        }
         bool unstable = false;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) unstable |= best[v].r != best[v].rlow;      // cutils.pyx:177 (by value)
