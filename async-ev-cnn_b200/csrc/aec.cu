@@ -475,7 +475,8 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
         p.S = n->surface; p.sstride = (long long)n->L[0].H * n->L[0].W; p.Hin = n->L[0].H; p.Win = n->L[0].W;
         p.wgt = l.wgt; p.bias = l.bias; p.Npad = l.Npad; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
         p.C = l.C; p.H = l.H; p.W = l.W; p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
-        k_conv_stencil<<<n->num_sms * 8, kThreads, 0, st>>>(p);
+        if (l.kh == 3 && l.kw == 3) k_conv_stencil<3, 3><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+        else k_conv_stencil<0, 0><<<n->num_sms * 8, kThreads, 0, st>>>(p);
         int rc = launch_check(n, "k_conv_stencil");
         return rc ? rc : prof_mark(n, st);
     }

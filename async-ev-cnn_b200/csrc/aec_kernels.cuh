@@ -1118,11 +1118,15 @@ struct StencilParams {
 };
 constexpr int kStencilMaxK = 64, kStencilMaxC = 64;
 
+// KH x KW > 0: compile-time window (3x3 for EFCN) - the loop unrolls and all surface loads are in flight together;
+// KH = KW = 0: run-time window sizes.
+template <int KH, int KW>
 __global__ void __launch_bounds__(kThreads) k_conv_stencil(StencilParams p)
 {
+    const int kh = KH > 0 ? KH : p.kh, kw = KW > 0 ? KW : p.kw;
     __shared__ __align__(16) float w_s[kStencilMaxK * kStencilMaxC];
     __shared__ __align__(16) float b_s[kStencilMaxC];
-    const int K = p.kh * p.kw;
+    const int K = kh * kw;
     for (int i = threadIdx.x; i < K * p.C; i += kThreads) w_s[i] = p.wgt[(i / p.C) * p.Npad + (i % p.C)];
     for (int i = threadIdx.x; i < p.C; i += kThreads) b_s[i] = p.bias[i];
     __syncthreads();
@@ -1139,20 +1143,27 @@ __global__ void __launch_bounds__(kThreads) k_conv_stencil(StencilParams p)
         const int y = site / p.W, x = site - y * p.W;
         const double *Sb = p.S + (long long)s * p.sstride;
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f), a = f;
-        int k = 0;
-        for (int ky = 0; ky < p.kh; ++ky)
-            for (int kx = 0; kx < p.kw; ++kx, ++k) {
-                const int iy = y + ky - p.pad_t, ix = x + kx - p.pad_l;
-                float v = 0.f, r = 0.f;
-                if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) {
-                    const double sv = Sb[(long long)iy * p.Win + ix];
-                    v = __double2float_rn(sv);
-                    r = sv > 0.0 ? 1.f : 0.f;
-                }
-                const float4 w = *reinterpret_cast<const float4 *>(&w_s[k * p.C + c]);
-                f.x = fmaf(v, w.x, f.x); f.y = fmaf(v, w.y, f.y); f.z = fmaf(v, w.z, f.z); f.w = fmaf(v, w.w, f.w);
-                a.x = fmaf(r, w.x, a.x); a.y = fmaf(r, w.y, a.y); a.z = fmaf(r, w.z, a.z); a.w = fmaf(r, w.w, a.w);
-            }
+        auto tap = [&](int ky, int kx) {
+            const int iy = y + ky - p.pad_t, ix = x + kx - p.pad_l;
+            return ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) ? Sb[(long long)iy * p.Win + ix] : 0.0;
+        };
+        auto acc = [&](int k, double sv) {
+            const float v = __double2float_rn(sv), r = sv > 0.0 ? 1.f : 0.f;
+            const float4 w = *reinterpret_cast<const float4 *>(&w_s[k * p.C + c]);
+            f.x = fmaf(v, w.x, f.x); f.y = fmaf(v, w.y, f.y); f.z = fmaf(v, w.z, f.z); f.w = fmaf(v, w.w, f.w);
+            a.x = fmaf(r, w.x, a.x); a.y = fmaf(r, w.y, a.y); a.z = fmaf(r, w.z, a.z); a.w = fmaf(r, w.w, a.w);
+        };
+        if constexpr (KH > 0 && KW > 0) {
+            double sv[KH * KW];
+#pragma unroll
+            for (int k = 0; k < KH * KW; ++k) sv[k] = tap(k / KW, k % KW);
+#pragma unroll
+            for (int k = 0; k < KH * KW; ++k) acc(k, sv[k]);
+        } else {
+            int k = 0;
+            for (int ky = 0; ky < kh; ++ky)
+                for (int kx = 0; kx < kw; ++kx, ++k) acc(k, tap(ky, kx));
+        }
         const float4 b = *reinterpret_cast<const float4 *>(&b_s[c]);
         f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
         const long long o = (long long)s * p.fstride + (long long)site * p.C + c;
