@@ -53,7 +53,7 @@ struct HostLayer {
     float *F = nullptr, *A = nullptr, *initF = nullptr;
     uint8_t *idx = nullptr, *initIdx = nullptr;
     float *Fp = nullptr, *Ap = nullptr, *initFp = nullptr;   // pool: copy of the conv maps at the argmax
-    uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr, *nzr = nullptr;
+    uint32_t *flags = nullptr, *front = nullptr, *signchg = nullptr, *nzr = nullptr, *skip = nullptr;
     uint32_t *sites = nullptr;      // this layer's work list (region of aec_net::sites)
     float *wgt = nullptr, *bias = nullptr;
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
@@ -77,6 +77,7 @@ struct aec_net {
     int *prev_ts = nullptr;
     uint8_t *active = nullptr, *mask = nullptr;
     uint32_t *sites = nullptr;
+    bool sweep_skip = true;              // the leak sweep leaves the sites alone that the step re-evaluates (AEC_SWEEP_SKIP=0: leak every live site)
     FrontLayer *front_table = nullptr;   // device copy of the per-layer frontier descriptors (k_frontier_all)
     int front_max_words = 0;
     int *counts = nullptr, *err_flag = nullptr;
@@ -406,7 +407,7 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
 }
 
 // Fills one leak-sweep table entry; returns the number of chunks (grid.x slots) the layer takes.
-static int fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0, bool dense_only = false)
+static int fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0, bool dense_only = false, bool use_skip = false)
 {
     if (l.type == AEC_LAYER_POOL) { o.F = l.Fp; o.A = l.Ap; o.signchg = nullptr; }
     else { o.F = l.F; o.A = l.A; o.signchg = l.signchg; }
@@ -414,6 +415,7 @@ static int fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0, bool 
     o.n4 = (int)(l.fstride / 4); o.chunk0 = chunk0;
     o.C = l.C; o.W = l.W; o.Ww = l.Ww; o.HWw = l.H * l.Ww;
     o.nzr = (!dense_only && l.C % 4 == 0) ? l.nzr : nullptr;     // a float4 of the sweep must not straddle sites
+    o.skip = use_skip ? l.skip : nullptr;
     o.c4 = l.C / 4;
     o.c4_shift = -1;
     o.wpc = 1;
@@ -549,6 +551,17 @@ static int run_eval(aec_net *n, int li, cudaStream_t st)
     return n->L[li].type == AEC_LAYER_CONV ? run_conv_eval(n, li, st) : run_pool_eval(n, li, st);
 }
 
+static int run_frontier_skip(aec_net *n, cudaStream_t st)
+{
+    if (!n->sweep_skip) return AEC_OK;
+    FrontAllParams p;
+    p.layers = n->front_table; p.n_layers = (int)n->L.size();
+    p.front0 = n->L[0].front; p.nzr0 = n->L[0].nzr; p.words0 = n->L[0].H * n->L[0].Ww;
+    p.max_words = n->front_max_words; p.active = n->active;
+    k_frontier_skip<<<n->S, kThreads, (size_t)3 * n->front_max_words * 4, st>>>(p);
+    return launch_check(n, "k_frontier_skip");
+}
+
 static int run_frontier_all(aec_net *n, cudaStream_t st)
 {
     FrontAllParams p;
@@ -632,6 +645,7 @@ extern "C" int aec_net_finalize(aec_net *n)
         const size_t bm = (size_t)l.H * l.Ww;
         if ((rc = dev_alloc(n, &l.front, S * bm, true))) return rc;
         if ((rc = dev_alloc(n, &l.nzr, S * bm, true))) return rc;
+        if ((rc = dev_alloc(n, &l.skip, S * bm, true))) return rc;
         if (l.type == AEC_LAYER_CONV) {
             if ((rc = dev_alloc_map(n, &l.F, S * l.fstride))) return rc;
             if ((rc = dev_alloc_map(n, &l.A, S * l.fstride))) return rc;
@@ -689,23 +703,25 @@ extern "C" int aec_net_finalize(aec_net *n)
             FrontLayer &f = tab[li];
             f.type = l.type; f.Hin = pv.H; f.Win = pv.W; f.WwIn = pv.Ww; f.H = l.H; f.W = l.W; f.Ww = l.Ww;
             f.kh = l.kh; f.kw = l.kw; f.pad_t = l.pad_t; f.pad_l = l.pad_l; f.stride = l.stride;
-            f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.sites = l.sites; f.counter = n->counts + li;
+            f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.skip = l.skip; f.sites = l.sites; f.counter = n->counts + li;
             mw = std::max(mw, std::max(pv.H * pv.Ww, std::max(pv.H * l.Ww, l.H * l.Ww)));
         }
         n->front_max_words = mw;
         if ((size_t)5 * mw * 4 > 200 * 1024) return fail(AEC_EINVAL, "frame too large for the frontier kernel's shared memory");
         if ((rc = dev_alloc(n, &n->front_table, tab.size(), false))) return rc;
         CU(cudaMemcpy(n->front_table, tab.data(), tab.size() * sizeof(FrontLayer), cudaMemcpyHostToDevice));
+        CU(cudaFuncSetAttribute(k_frontier_skip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)3 * mw * 4, 48 * 1024)));
         CU(cudaFuncSetAttribute(k_frontier_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)5 * mw * 4, 48 * 1024)));
     }
 
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
+    { const char *e = getenv("AEC_SWEEP_SKIP"); n->sweep_skip = !(e && atoi(e) == 0); }
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
     int chunk0 = 0, nc = 0;
     for (int pass = 0; pass < 2; ++pass) {
         for (auto &l : n->L)
             if (l.type == (pass == 0 ? AEC_LAYER_CONV : AEC_LAYER_POOL)) {
-                chunk0 += fill_sweep_layer(l, n->sweep_all.L[nc], chunk0);
+                chunk0 += fill_sweep_layer(l, n->sweep_all.L[nc], chunk0, false, n->sweep_skip);
                 ++nc;
             }
         if (pass == 0) { n->sweep_nconv = nc; n->sweep_conv_chunks = chunk0; }
@@ -854,6 +870,7 @@ static int step_body(aec_net *n, const int32_t *ev, const int32_t *off, cudaStre
 {
     int rc;
     if ((rc = run_integrate(n, ev, off, st))) return rc;
+    if ((rc = run_frontier_skip(n, st))) return rc;       // which sites the step re-evaluates anyway: the sweep skips them
     if ((rc = run_sweep(n, -1, st))) return rc;
     if ((rc = run_frontier_all(n, st))) return rc;
     for (int li = 1; li < (int)n->L.size(); ++li)
@@ -1223,31 +1240,34 @@ extern "C" int aec_net_tc_timing(aec_net *n, int enable, int layer, unsigned lon
     return AEC_OK;
 }
 
-extern "C" int aec_net_sweep_stats(aec_net *n, unsigned long long *out6)
+extern "C" int aec_net_sweep_stats(aec_net *n, unsigned long long *out8)
 {
     NEED_FINAL(n);
-    if (!out6) return fail(AEC_EINVAL, "sweep_stats: out is NULL");
+    if (!out8) return fail(AEC_EINVAL, "sweep_stats: out is NULL");
     unsigned long long nz = 0, tot = 0;
     int rc = aec_net_count_nonzero_rate_groups(n, &nz, &tot);
     if (rc) return rc;
-    out6[0] = nz;
-    out6[1] = tot;
-    unsigned long long live_conv = 0, all_conv = 0, live_pool = 0, all_pool = 0;
+    out8[0] = nz;
+    out8[1] = tot;
+    unsigned long long live_conv = 0, all_conv = 0, live_pool = 0, all_pool = 0, swept_conv = 0, swept_pool = 0;
     for (auto &l : n->L) {
         if (l.type == AEC_LAYER_INTEGRATION) continue;
         const long long words = (long long)n->S * l.H * l.Ww;
-        CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
-        k_count_bits<<<std::min<long long>((words + kThreads - 1) / kThreads, (long long)n->num_sms * 8), kThreads>>>(l.nzr, words, n->accum + 31);
-        if ((rc = launch_check(n, "k_count_bits"))) return rc;
-        unsigned long long bits = 0;
-        CU(cudaMemcpy(&bits, n->accum + 31, sizeof bits, cudaMemcpyDeviceToHost));
+        const int blocks = (int)std::min<long long>((words + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
+        unsigned long long bits[2] = {0, 0};
+        for (int pass = 0; pass < 2; ++pass) {          // 0: live sites; 1: live sites the sweep does not skip (skip[] of the last step)
+            CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
+            k_count_bits<<<blocks, kThreads>>>(l.nzr, pass == 1 && n->sweep_skip ? l.skip : nullptr, words, n->accum + 31);
+            if ((rc = launch_check(n, "k_count_bits"))) return rc;
+            CU(cudaMemcpy(&bits[pass], n->accum + 31, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        }
         const unsigned long long all = (unsigned long long)n->S * l.H * l.W * l.C;
-        if (l.C % 4) bits = (unsigned long long)n->S * l.H * l.W;      // dense path of the sweep: every site is read
-        if (l.type == AEC_LAYER_CONV) { live_conv += bits * l.C; all_conv += all; }
-        else { live_pool += bits * l.C; all_pool += all; }
+        if (l.C % 4) bits[0] = bits[1] = (unsigned long long)n->S * l.H * l.W;      // dense path of the sweep: every site is read
+        if (l.type == AEC_LAYER_CONV) { live_conv += bits[0] * l.C; swept_conv += bits[1] * l.C; all_conv += all; }
+        else { live_pool += bits[0] * l.C; swept_pool += bits[1] * l.C; all_pool += all; }
     }
     CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
-    out6[2] = live_conv; out6[3] = all_conv; out6[4] = live_pool; out6[5] = all_pool;
+    out8[2] = live_conv; out8[3] = all_conv; out8[4] = live_pool; out8[5] = all_pool; out8[6] = swept_conv; out8[7] = swept_pool;
     return AEC_OK;
 }
 

@@ -344,6 +344,7 @@ struct SweepLayer {
     float *F, *A;
     uint32_t *signchg;
     const uint32_t *nzr;  // [S][H*Ww] sites that can have a non-zero rate (nullptr: dense path)
+    const uint32_t *skip; // [S][H*Ww] sites this step re-evaluates anyway (k_frontier_skip); nullptr: leak every live site
     long long fstride;   // floats per stream (multiple of 4)
     int n4;              // float4 per stream
     int chunk0;          // first chunk index of this layer
@@ -417,7 +418,12 @@ __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__
         const int w0 = (chunk - L.chunk0) * L.wpc, w1 = min(L.HWw, w0 + L.wpc);
         const uint32_t *nz = L.nzr + (long long)s * L.HWw;
         uint32_t bits = 0u;
-        if ((int)threadIdx.x < w1 - w0) bits = __ldg(nz + w0 + threadIdx.x);
+        if ((int)threadIdx.x < w1 - w0) {
+            bits = __ldg(nz + w0 + threadIdx.x);
+            // a site that this step re-evaluates gets F and A overwritten and is on the layer's frontier whatever its
+            // signs do: leaking it first would be wasted traffic (at steady state that is every live site of conv2..conv7)
+            if (L.skip) bits &= ~__ldg(L.skip + (long long)s * L.HWw + w0 + threadIdx.x);
+        }
         int total;
         int off = block_excl_scan(__popc(bits), s_scan, &total);
         if (total == 0) return;
@@ -677,6 +683,7 @@ struct FrontLayer {
     int Hin, Win, WwIn, H, W, Ww;
     int kh, kw, pad_t, pad_l, stride;
     uint32_t *front, *signchg, *flags, *nzr;
+    uint32_t *skip;               // [S][H*Ww] written by k_frontier_skip: a subset of this step's work set, known before the leak sweep
     uint32_t *sites;
     int *counter;
 };
@@ -802,6 +809,86 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
         emit_sites(N, L.H, L.W, L.Ww, (uint32_t)s * (uint32_t)(L.H * L.W), L.sites, L.counter, scratch);
         __syncthreads();
         for (int i = tid; i < nout; i += kThreads) bufB[i] = Z[i];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3': the part of every layer's work set that is known BEFORE the leak sweep.  The exact frontier of a conv layer
+// is dilate(previous frontier) united with the sign flips the sweep finds; this kernel runs the same bitmap chain
+// with the flips left out (event pixels and pixel deaths from k_integrate, dilation, pool windows, sticky flags).
+// Every operation is monotone, so skip[l] is a subset of the sites / windows layer l re-evaluates in this step -
+// which the leak sweep may therefore leave alone (their F, A or (Fp, Ap) are overwritten, and they are on the
+// layer's frontier regardless of their signs).  Nothing but skip[] is written.  One CTA per stream.
+// Dynamic shared memory: 3 * max_words * 4 bytes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_frontier_skip(FrontAllParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);        // previous layer's (flip-free) frontier
+    uint32_t *Hd = bufA + p.max_words;                              // scratch (horizontal dilation)
+    uint32_t *N = Hd + p.max_words;                                 // this layer's set
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (!p.active[s]) return;                                       // the sweep does not touch an idle stream
+    for (int i = tid; i < p.words0; i += kThreads) bufA[i] = p.front0[(long long)s * p.words0 + i];
+    __syncthreads();
+    for (int li = 1; li < p.n_layers; ++li) {
+        const FrontLayer L = p.layers[li];
+        const int nout = L.H * L.Ww;
+        const uint32_t lastmask = (L.W & 31) ? ((1u << (L.W & 31)) - 1u) : 0xffffffffu;
+        uint32_t *skip = L.skip + (long long)s * nout;
+        if (L.type == 1) {
+            for (int i = tid; i < L.Hin * L.Ww; i += kThreads) {
+                const int y = i / L.Ww, w = i - y * L.Ww;
+                uint32_t acc = 0u;
+                for (int d = L.pad_l - L.kw + 1; d <= L.pad_l; ++d) acc |= row_shift(bufA + y * L.WwIn, L.WwIn, w, d);
+                if (w == L.Ww - 1) acc &= lastmask;
+                Hd[i] = acc;
+            }
+            __syncthreads();
+            for (int i = tid; i < nout; i += kThreads) {
+                const int y = i / L.Ww, w = i - y * L.Ww;
+                uint32_t acc = 0u;
+                for (int d = L.pad_t - L.kh + 1; d <= L.pad_t; ++d) {
+                    const int yi = y - d;
+                    if (yi >= 0 && yi < L.Hin) acc |= Hd[yi * L.Ww + w];
+                }
+                N[i] = acc;
+                skip[i] = acc;
+            }
+        } else {
+            const uint32_t *fl = L.flags + (long long)s * nout;
+            for (int i = tid; i < nout; i += kThreads) {
+                const int oy = i / L.Ww, w = i - oy * L.Ww;
+                uint32_t hit = 0u;
+                if (L.kh == 2 && L.kw == 2 && L.stride == 2) {
+                    const uint32_t *r0 = bufA + (2 * oy) * L.WwIn, *r1 = r0 + L.WwIn;
+                    uint32_t lo = (2 * w < L.WwIn) ? (r0[2 * w] | r1[2 * w]) : 0u;
+                    uint32_t hi = (2 * w + 1 < L.WwIn) ? (r0[2 * w + 1] | r1[2 * w + 1]) : 0u;
+                    lo |= lo >> 1;
+                    hi |= hi >> 1;
+                    hit = compress_even_bits(lo) | (compress_even_bits(hi) << 16);
+                } else {
+                    for (int b = 0; b < 32; ++b) {
+                        const int ox = w * 32 + b;
+                        if (ox >= L.W) break;
+                        bool any = false;
+                        for (int dy = 0; dy < L.kh && !any; ++dy)
+                            for (int dx = 0; dx < L.kw; ++dx) {
+                                const int iy = oy * L.stride + dy, ix = ox * L.stride + dx;
+                                if ((bufA[iy * L.WwIn + (ix >> 5)] >> (ix & 31)) & 1u) { any = true; break; }
+                            }
+                        if (any) hit |= 1u << b;
+                    }
+                }
+                if (w == L.Ww - 1) hit &= lastmask;
+                const uint32_t wset = hit | fl[i];        // maxpool.py:118-126: hit windows and still-flagged windows
+                N[i] = wset;
+                skip[i] = wset;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nout; i += kThreads) bufA[i] = N[i];
         __syncthreads();
     }
 }
@@ -1252,10 +1339,12 @@ __global__ void __launch_bounds__(kThreads) k_count_nz4(const __grid_constant__ 
 }
 
 // K9b: measurement helper - number of set bits of a [S][words] bitmap (live sites of a layer).
-__global__ void __launch_bounds__(kThreads) k_count_bits(const uint32_t *bm, long long words, unsigned long long *out)
+// With `notmask`: bits of bm that are clear in notmask (live sites the leak sweep does not skip).
+__global__ void __launch_bounds__(kThreads) k_count_bits(const uint32_t *bm, const uint32_t *notmask, long long words, unsigned long long *out)
 {
     int cnt = 0;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < words; i += (long long)gridDim.x * kThreads) cnt += __popc(bm[i]);
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < words; i += (long long)gridDim.x * kThreads)
+        cnt += __popc(notmask ? bm[i] & ~notmask[i] : bm[i]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);

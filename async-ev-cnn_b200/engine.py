@@ -280,12 +280,13 @@ class EventNetCuda:
 
     def sweep_stats(self):
         """Leak-sweep work of the current state: dict with the fraction of conv-map 16-byte groups whose rate is
-        non-zero, and the conv / pool-copy elements at live (non-zero-rate bit set) sites."""
-        buf = np.zeros(6, np.uint64)
+        non-zero, the conv / pool-copy elements at live (non-zero-rate bit set) sites, and the live elements the sweep
+        really touches (`swept_*`: live sites minus those the last step re-evaluated anyway, which the sweep skips)."""
+        buf = np.zeros(8, np.uint64)
         N.check(self._lib.aec_net_sweep_stats(self._h, _ptr(buf)))
         v = [int(x) for x in buf]
         return {"nz_groups": v[0], "groups": v[1], "live_conv_elems": v[2], "conv_elems": v[3], "live_pool_elems": v[4],
-                "pool_elems": v[5]}
+                "pool_elems": v[5], "swept_conv_elems": v[6], "swept_pool_elems": v[7]}
 
     def tc_layers(self):
         """Indices of the conv layers that run on the tensor-core kernel (previous layer a map with C % 4 == 0, kh*kw <= 32)."""

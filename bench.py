@@ -179,13 +179,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def algorithmic_bytes(net, sites_per_step, sw, streams, batch):
     """SURVEY 8(d) / BASELINE.md section 4 per step over all streams, with the leak term stated for what the
-    implemented algorithm needs: the rate A is read at the sites whose non-zero-rate bit is set (4 B/elem),
-    F is read and written only in the 16-byte groups whose rate is non-zero (8 B/elem), plus the bitmaps.
+    implemented algorithm needs: A and F are read and F written (12 B/elem) at the live sites (non-zero-rate bit
+    set) that the step does not re-evaluate anyway - a re-evaluated site gets F and A overwritten, so its leak is
+    not needed (`swept_conv_elems`) - plus the bitmaps (non-zero-rate, skip, sign-change).
     The pool layers' (Fp, Ap) copies are an implementation choice and are NOT counted as algorithmic."""
     shapes = net.shapes()
     nz4 = sw["nz_groups"] / max(1, sw["groups"])
     bitmaps = sum(h * ((w + 31) // 32) * 4 for nm, (c, h, w) in zip(net.names, shapes) if "conv" in nm) * streams
-    leak = 4.0 * sw["live_conv_elems"] + 8.0 * nz4 * sw["conv_elems"] + bitmaps
+    leak = 12.0 * sw.get("swept_conv_elems", sw["live_conv_elems"]) + 3 * bitmaps
     surface = streams * 2 * 8 * H * W
     ev = streams * 12 * batch
     conv = pool = 0.0
@@ -350,9 +351,10 @@ def native_arm(args):
                     "algorithmic_bytes_per_launch": ab["leak_sweep"], "kernel_ms": sweep_ms,
                     "kernel_share_of_step": sweep_ms / step_ms_prof if step_ms_prof else None,
                     "live_site_fraction": sw["live_conv_elems"] / max(1, sw["conv_elems"]),
+                    "swept_fraction": sw.get("swept_conv_elems", sw["live_conv_elems"]) / max(1, sw["conv_elems"]),
                     "nonzero_rate_group_fraction": sw["nz_groups"] / max(1, sw["groups"]),
-                    "unaccounted": "the pool layers' (Fp, Ap) copies swept by the same launch (live %.3g of %.3g elements x 12 B) are not in the algorithmic bytes" % (
-                        sw["live_pool_elems"], sw["pool_elems"]),
+                    "unaccounted": "the pool layers' (Fp, Ap) copies swept by the same launch (%.3g of %.3g elements x 12 B) are not in the algorithmic bytes" % (
+                        sw.get("swept_pool_elems", sw["live_pool_elems"]), sw["pool_elems"]),
                     "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms_total / K * 1e-3) / 1e9,
                                    "frac": ab["total"] / (ms_total / K * 1e-3) / 1e9 / peak,
                                    "survey_8d": {"note": "SURVEY 8(d) formula as written (dense leak pass, 12 B per conv element, + measured frontier terms): "

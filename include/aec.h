@@ -245,12 +245,13 @@ int aec_decode_ndata(int device, const uint8_t *raw, const long long *byte_offse
                      int crop, int new_h, int new_w, int32_t *events_yxt_out, int32_t *polarity_out, int32_t *counts_out);
 
 /*
- * Measurement helper for the leak sweep's roofline.  out6 = { 16-byte groups of the conv rate maps holding a
- * non-zero rate, all such groups, conv-map elements at sites whose non-zero-rate bit is set (the elements
- * whose rate the sweep has to read), all conv-map elements, the same two for the pool layers' (Fp, Ap)
- * copies }.  Synchronises.
+ * Measurement helper for the leak sweep's roofline.  out8 = { 16-byte groups of the conv rate maps holding a
+ * non-zero rate, all such groups, conv-map elements at sites whose non-zero-rate bit is set (live elements),
+ * all conv-map elements, the same two for the pool layers' (Fp, Ap) copies, and the live conv / pool-copy
+ * elements the sweep really touches: live sites minus the sites the last step re-evaluated anyway (the sweep
+ * skips those: their F, A are overwritten in the same step, conv2d.py:118-123) }.  Synchronises.
  */
-int aec_net_sweep_stats(aec_net *net, unsigned long long *out6);
+int aec_net_sweep_stats(aec_net *net, unsigned long long *out8);
 
 /*
  * Measurement helper for the tensor-core conv kernel: with out16 == NULL, enables (enable != 0) or
