@@ -559,7 +559,8 @@ static int run_frontier_skip(aec_net *n, cudaStream_t st)
     p.front0 = n->L[0].front; p.nzr0 = n->L[0].nzr; p.words0 = n->L[0].H * n->L[0].Ww;
     p.max_words = n->front_max_words; p.active = n->active;
     k_frontier_skip<<<n->S, kThreads, (size_t)3 * n->front_max_words * 4, st>>>(p);
-    return launch_check(n, "k_frontier_skip");
+    int rc = launch_check(n, "k_frontier_skip");
+    return rc ? rc : prof_mark(n, st);
 }
 
 static int run_frontier_all(aec_net *n, cudaStream_t st)

@@ -424,9 +424,9 @@ __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__
             // signs do: leaking it first would be wasted traffic (at steady state that is every live site of conv2..conv7)
             if (L.skip) bits &= ~__ldg(L.skip + (long long)s * L.HWw + w0 + threadIdx.x);
         }
+        if (!__syncthreads_or(bits != 0u)) return;       // nothing to leak in this chunk (the common case for skipped layers)
         int total;
         int off = block_excl_scan(__popc(bits), s_scan, &total);
-        if (total == 0) return;
         if (bits) {
             const int w = w0 + threadIdx.x;
             const int y = w / L.Ww, xb = (w - y * L.Ww) * 32;

@@ -5,6 +5,7 @@ One reference network object is one stream (src/models/event_numpy.py:53-105); t
 Python veneer over the C ABI (include/aec.h): numpy in, numpy out, no arithmetic on the host.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -263,7 +264,8 @@ class EventNetCuda:
     # -- measurement ---------------------------------------------------------------------------
     def slot_names(self):
         """Names of the launches of one step, in order (matches aec_net_read_profile slots)."""
-        return ["surface", "leak_sweep", "all.frontier"] + [nm + ".eval" for nm in self.names[1:]] + ["head"]
+        skip = ["skip.frontier"] if os.environ.get("AEC_SWEEP_SKIP", "1") != "0" else []      # k_frontier_skip (before the sweep)
+        return ["surface"] + skip + ["leak_sweep", "all.frontier"] + [nm + ".eval" for nm in self.names[1:]] + ["head"]
 
     def profile(self, enable=True):
         N.check(self._lib.aec_net_profile(self._h, 1 if enable else 0))

@@ -375,3 +375,32 @@ def test_diagnostics_api_is_consistent_with_the_maps():
         assert d["ctas"] > 0 and d["mma_total"] > 0 and d["prod_total"] > 0 and d["epi_total"] > 0, (nm, d)
     assert np.array_equal(ad.step(g.events(7)).shape, g.z["heads"][7].shape)
     net.close()
+
+
+def test_sweep_skipping_changes_no_bit(monkeypatch):
+    """The leak sweep leaves alone the sites that the same step re-evaluates (k_frontier_skip computes a subset of
+    every layer's work set before the sweep).  With the skip switched off (AEC_SWEEP_SKIP=0) every map, index and
+    frontier must come out bit-identical, on a float net with sign flips and sticky pool flags."""
+    g = Golden(golden_path("small32_float"))
+    nets = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AEC_SWEEP_SKIP", flag)
+        nets.append(EventNetCuda(g.height, g.width, g.layers, g.weights(), g.leak, g.alpha, "SAME", n_streams=2))
+    n_steps = min(120, g.z["heads"].shape[0])
+    for t in range(n_steps):
+        ev = g.events(t)
+        per = [ev, ev if t % 3 else None]
+        ha, hb = nets[0].step(per), nets[1].step(per)
+        assert np.array_equal(ha[0], hb[0]), "step %d head" % t
+        if t % 10 == 9 or t == n_steps - 1:
+            for s in range(2):
+                for i in range(len(nets[0].names)):
+                    sa, sb = nets[0].state(i, s), nets[1].state(i, s)
+                    for key in sa:
+                        assert np.array_equal(sa[key], sb[key]), "step %d stream %d layer %s %s" % (t, s, nets[0].names[i], key)
+                    assert np.array_equal(nets[0].frontier(i, s), nets[1].frontier(i, s))
+    st = nets[0].sweep_stats()
+    assert st["swept_conv_elems"] <= st["live_conv_elems"]
+    assert nets[1].sweep_stats()["swept_conv_elems"] == nets[1].sweep_stats()["live_conv_elems"]
+    for n in nets:
+        n.close()
