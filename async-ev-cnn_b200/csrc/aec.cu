@@ -461,7 +461,8 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     static const int dbg = getenv("AEC_TC_DEBUG") ? atoi(getenv("AEC_TC_DEBUG")) : 0;
     p.debug = dbg;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
-    tc::k_conv_eval_tc<<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    if (l.KB >= 10) tc::k_conv_eval_tc<true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    else tc::k_conv_eval_tc<false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st);
 }
@@ -755,20 +756,21 @@ extern "C" int aec_net_finalize(aec_net *n)
             }
         if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
         if (tc_max) {
-            cudaError_t e = cudaFuncSetAttribute(tc::k_conv_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max);
-            if (e != cudaSuccess) return fail(AEC_ECUDA, "cannot opt in to %zu bytes of dynamic shared memory for the tensor-core conv kernel: %s", tc_max, cudaGetErrorString(e));
-        }
-        if (tc_max) {
-            // the role split (setmaxnreg) must fit the register pool the CTA is launched with, or the
-            // producers' increase would wait forever
-            cudaFuncAttributes fa;
-            CU(cudaFuncGetAttributes(&fa, tc::k_conv_eval_tc));
-            const int pool = fa.numRegs * tc::kTcThreads;
-            const int want = 128 * tc::kRegsEpi + 128 * tc::kRegsCtl + 384 * tc::kRegsProd;
-            if (want > pool || fa.numRegs > tc::kRegsProd || fa.numRegs < tc::kRegsEpi)
-                return fail(AEC_EINVAL, "tensor-core conv kernel was built with %d registers/thread; the role split needs %d of %d", fa.numRegs, want, pool);
-            if (tc_max + fa.sharedSizeBytes > 227 * 1024)
-                return fail(AEC_EINVAL, "tensor-core conv kernel needs %zu + %zu bytes of shared memory", tc_max, (size_t)fa.sharedSizeBytes);
+            const void *variants[2] = {(const void *)tc::k_conv_eval_tc<false>, (const void *)tc::k_conv_eval_tc<true>};
+            for (const void *fn : variants) {
+                cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max);
+                if (e != cudaSuccess) return fail(AEC_ECUDA, "cannot opt in to %zu bytes of dynamic shared memory for the tensor-core conv kernel: %s", tc_max, cudaGetErrorString(e));
+                // the role split (setmaxnreg) must fit the register pool the CTA is launched with, or the
+                // producers' increase would wait forever
+                cudaFuncAttributes fa;
+                CU(cudaFuncGetAttributes(&fa, fn));
+                const int pool = fa.numRegs * tc::kTcThreads;
+                const int want = 128 * tc::kRegsEpi + 128 * tc::kRegsCtl + 384 * tc::kRegsProd;
+                if (want > pool || fa.numRegs > tc::kRegsProd || fa.numRegs < tc::kRegsEpi)
+                    return fail(AEC_EINVAL, "tensor-core conv kernel was built with %d registers/thread; the role split needs %d of %d", fa.numRegs, want, pool);
+                if (tc_max + fa.sharedSizeBytes > 227 * 1024)
+                    return fail(AEC_EINVAL, "tensor-core conv kernel needs %zu + %zu bytes of shared memory", tc_max, (size_t)fa.sharedSizeBytes);
+            }
         }
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));
         n->conv_eval_blocks[0] = std::max(1, b) * n->num_sms;

@@ -310,6 +310,7 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
 // The weight stages come first: the A descriptor always spans 128 rows, so with Mrows < 128 it reads
 // past the tile into whatever follows (the next stage / the site stages); those rows only feed
 // accumulator lanes >= Mrows, which the epilogue never reads.
+template <bool kFastDecode>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
     extern __shared__ unsigned char tc_smem_raw[];
@@ -549,30 +550,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         }
       } else if (warp == kSiteWarp) {
         // ===================== site decoder =====================
+        // kFastDecode (layers with long units, KB >= 10): measured 3-4 % faster there, but 2-8 % slower for the short
+        // units of the first two tensor-core layers, which keep the simple loop (profiles/r1e_summary.md).
+        const double inv_hw = 1.0 / (double)HW, inv_w = 1.0 / (double)p.W;
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
             const int blk = unit / n_mgroups;
             const int buf = ul % kSiteRing;
             const uint32_t us = (uint32_t)(ul / kSiteRing);
-            if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
-            for (int i = lane; i < kUnitSites; i += 32) {
-                const long long gi = (long long)blk * kUnitSites + i;
-                SiteSrc q;
-                q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
-                long long dst = -1;
-                if (gi < n_sites) {
-                    const uint32_t e = p.sites[gi];
-                    const int s = (int)(e / (uint32_t)HW);
-                    const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
-                    const int y = site / p.W, x = site - y * p.W;
-                    q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
-                    for (int ky = 0, tap = 0; ky < p.kh; ++ky)
-                        for (int kx = 0; kx < p.kw; ++kx, ++tap)
-                            if ((unsigned)(y + ky - p.pad_t) < (unsigned)p.Hin && (unsigned)(x + kx - p.pad_l) < (unsigned)p.Win) q.taps |= 1u << tap;
-                    dst = ((long long)s * p.fstride + (long long)site * p.C) * 4;
+            if constexpr (kFastDecode) {
+                // The unit's work-list entries are read before the wait for the ring slot, all four per lane at once (one
+                // trip to memory per unit instead of four dependent ones), and decoded with reciprocal multiplications and
+                // per-row / per-column validity masks instead of integer divisions and a kh x kw loop: the decoder is a
+                // single warp and must not need more cycles per unit than a short (5-pass) unit takes.
+                uint32_t ent[kUnitSites / 32];
+    #pragma unroll
+                for (int k = 0; k < kUnitSites / 32; ++k) {
+                    const long long gi = (long long)blk * kUnitSites + lane + 32 * k;
+                    ent[k] = gi < n_sites ? __ldg(p.sites + gi) : 0xffffffffu;
                 }
-                s_src[buf][i] = q;
-                s_dst[buf][i] = dst;
+                if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
+    #pragma unroll
+                for (int k = 0; k < kUnitSites / 32; ++k) {
+                    const int i = lane + 32 * k;
+                    SiteSrc q;
+                    q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
+                    long long dst = -1;
+                    if (ent[k] != 0xffffffffu) {
+                        const uint32_t e = ent[k];
+                        int s = (int)__double2uint_rz(__uint2double_rn(e) * inv_hw);       // e / HW, off by at most one
+                        int site = (int)(e - (uint32_t)s * (uint32_t)HW);
+                        if (site < 0) { --s; site += HW; } else if (site >= HW) { ++s; site -= HW; }
+                        int y = (int)__double2uint_rz(__uint2double_rn((uint32_t)site) * inv_w);
+                        int x = site - y * p.W;
+                        if (x < 0) { --y; x += p.W; } else if (x >= p.W) { ++y; x -= p.W; }
+                        q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
+                        uint32_t colbits = 0u;
+                        for (int kx = 0; kx < p.kw; ++kx)
+                            if ((unsigned)(x + kx - p.pad_l) < (unsigned)p.Win) colbits |= 1u << kx;
+                        for (int ky = 0; ky < p.kh; ++ky)
+                            if ((unsigned)(y + ky - p.pad_t) < (unsigned)p.Hin) q.taps |= colbits << (ky * p.kw);
+                        dst = ((long long)s * p.fstride + (long long)site * p.C) * 4;
+                    }
+                    s_src[buf][i] = q;
+                    s_dst[buf][i] = dst;
+                }
+            } else {
+                if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
+                for (int i = lane; i < kUnitSites; i += 32) {
+                    const long long gi = (long long)blk * kUnitSites + i;
+                    SiteSrc q;
+                    q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
+                    long long dst = -1;
+                    if (gi < n_sites) {
+                        const uint32_t e = p.sites[gi];
+                        const int s = (int)(e / (uint32_t)HW);
+                        const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
+                        const int y = site / p.W, x = site - y * p.W;
+                        q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
+                        for (int ky = 0, tap = 0; ky < p.kh; ++ky)
+                            for (int kx = 0; kx < p.kw; ++kx, ++tap)
+                                if ((unsigned)(y + ky - p.pad_t) < (unsigned)p.Hin && (unsigned)(x + kx - p.pad_l) < (unsigned)p.Win) q.taps |= 1u << tap;
+                        dst = ((long long)s * p.fstride + (long long)site * p.C) * 4;
+                    }
+                    s_src[buf][i] = q;
+                    s_dst[buf][i] = dst;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_si_full[buf]));
