@@ -461,7 +461,7 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     static const int dbg = getenv("AEC_TC_DEBUG") ? atoi(getenv("AEC_TC_DEBUG")) : 0;
     p.debug = dbg;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
-    if (l.KB >= (getenv("AEC_TC_FASTDEC_KB") ? atoi(getenv("AEC_TC_FASTDEC_KB")) : 10)) tc::k_conv_eval_tc<true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    if (l.KB >= (getenv("AEC_TC_FASTDEC_KB") ? atoi(getenv("AEC_TC_FASTDEC_KB")) : 10) || (l.m_tiles > 1 && !getenv("AEC_TC_FASTDEC_KB"))) tc::k_conv_eval_tc<true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else tc::k_conv_eval_tc<false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st);

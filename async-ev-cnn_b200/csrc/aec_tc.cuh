@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         }
       } else if (warp == kSiteWarp) {
         // ===================== site decoder =====================
-        // kFastDecode (layers with long units, KB >= 10): measured 3-4 % faster there, but 2-8 % slower for the short
+        // kFastDecode (layers with long units or several weight tiles): measured 3-4 % faster there, but 2-8 % slower for the short
         // units of the first two tensor-core layers, which keep the simple loop (profiles/r1e_summary.md).
         const double inv_hw = 1.0 / (double)HW, inv_w = 1.0 / (double)p.W;
         for (int ul = 0; ul < n_units_cta; ++ul) {
