@@ -97,7 +97,7 @@ struct aec_net {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     unsigned long long async_calls = 0;
     float *head_cur = nullptr;     // where k_head writes (n->head, or a slot's buffer)
-    // CUDA graph of one step (27 launches replayed with one call; only the event pointers of the surface kernel and
+    // CUDA graph of one step (17 launches for EFCN replayed with one call; only the event pointers of the surface kernel and
     // the output pointer of the head kernel change between replays and are patched in place)
     struct StepGraph {
         cudaGraph_t graph = nullptr;
