@@ -87,3 +87,33 @@ def test_stress_config_davis346_deeper_variant_against_live_oracle():
     print("\n[parity] stress 256x320 deeper EFCN: %r" % mm)
     assert net.head_shape == (8, 10, 110)
     net.close()
+
+
+@pytest.mark.parametrize("kind", ["edge", "uniform"])
+def test_efcn_sweep_skipping_is_bit_neutral_at_steady_state(kind, monkeypatch):
+    """EFCN 160x224 run into its steady state (the regime where the sweep skips most of its work): every head,
+    map, index, flag and frontier must be bit-identical with the skip bitmaps switched off (AEC_SWEEP_SKIP=0)."""
+    wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
+    S, steps = 6, 180
+    evs = P.synthetic_events(kind, S, steps, 200, H, W, seed=17)
+    nets = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AEC_SWEEP_SKIP", flag)
+        nets.append(EventNetCuda(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=S))
+    for t in range(steps):
+        per = [evs[s, t] if (s + t) % 13 else None for s in range(S)]      # an idle stream now and then
+        ha, hb = nets[0].step(per), nets[1].step(per)
+        assert np.array_equal(ha, hb), "step %d heads differ" % t
+        if t == 90:
+            for n in nets:
+                n.reset(stream_mask=[0, 1, 0, 0, 0, 0])                    # one stream restarts mid-run
+    for s in (0, 1, S - 1):
+        for i in range(len(nets[0].names)):
+            sa, sb = nets[0].state(i, s), nets[1].state(i, s)
+            for key in sa:
+                assert np.array_equal(sa[key], sb[key]), "stream %d layer %s %s" % (s, nets[0].names[i], key)
+            assert np.array_equal(nets[0].frontier(i, s), nets[1].frontier(i, s))
+    st = nets[0].sweep_stats()
+    assert st["swept_conv_elems"] < st["live_conv_elems"], "at steady state the skip bitmaps must remove work"
+    for n in nets:
+        n.close()
