@@ -136,7 +136,8 @@ def workload_config(args, streams):
                         "synthetic %s streams, random-init weights" % (args.batch, args.kind),
             "streams_per_gpu": streams, "batch_event_size": args.batch, "stream_kind": args.kind, "frame": [H, W],
             "leak": LEAK, "alpha": ALPHA, "preroll_steps": args.preroll,
-            "l2": "inputs larger than L2: %.1f GB of stream state per GPU is swept every step (L2 = 126 MB)" % (streams * 10.2e-3)}
+            "l2": "inputs larger than L2: %.1f GB of stream state per GPU, of which every step reads or writes several GB "
+                  "(re-evaluated sites, pool windows, the leak sweep; roofline_hbm.whole_step); L2 = 126 MB" % (streams * 12.1e-3)}
 
 
 # ------------------------------------------------------------------------------------------------
