@@ -20,6 +20,9 @@
 // What bounds it (profiles/r1c_summary.md, r1d_summary.md): per K block the tensor core reads 12 x 12 KB
 // of operands, the producers store a 64 KB site stage and the loader 32 KB of weights - 240 KB per 1536
 // cycles, the measured shared-memory ceiling (~94 B/cycle of MMA reads + ~64 B/cycle of stores).
+// At steady state (profiles/r1e_summary.md) the short-unit layers are additionally bounded by the support roles:
+// with gathers, stores and MMAs knocked out conv2 still takes 72 % of its time (decoder ~8.5 k cycles per unit,
+// epilogue ~7.4 k, against a 10.9 k-cycle unit).
 //
 // Precision: north_star asks for float32 maps within 1e-4 relative, and the oracle's pool ties must
 // stay exact, so a bare TF32 product (10-bit mantissa) is not enough.  Every operand is split into
