@@ -121,3 +121,19 @@ def test_runner_feeds_chunks_and_resets_per_sample(capsys):
             want = oracle.step(chunk)
         assert np.allclose(outs[i], want.reshape(outs[i].shape), rtol=1e-4, atol=1e-5)
     assert "sec/example" in capsys.readouterr().out
+
+
+def test_run_networks_cli_with_the_efcn_config(capsys):
+    """python -m async_ev_cnn_b200.run_networks -c configs/efcn_event_cuda.yml (run_networks.py:15-59): the reference's
+    YAML with `network: YoloEventCuda`; no dataset on disk -> seeded synthetic recordings, centre-cropped 172x232 -> 160x224."""
+    import os
+    from async_ev_cnn_b200.run_networks import main
+    yml = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "efcn_event_cuda.yml")
+    outs = main(["-c", yml, "--max_samples", "1"])
+    assert len(outs) == 1 and outs[0].shape == (5, 7, 110) and np.isfinite(outs[0]).all()
+    text = capsys.readouterr().out
+    assert "sec/example" in text and "Mean fw time" in text
+    outs2 = main(["-c", yml, "--max_samples", "2", "--n_streams", "2", "--batch_event_size", "500"])
+    assert len(outs2) == 1 and outs2[0].shape == (2, 5, 7, 110) and np.isfinite(outs2[0]).all()
+    with pytest.raises(SystemExit):
+        main(["-c", yml, "--network", "YoloFrameTf"])
