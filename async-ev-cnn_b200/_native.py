@@ -17,10 +17,10 @@ SYMBOLS = [
     "aec_last_error", "aec_version", "aec_net_create", "aec_net_add_conv", "aec_net_add_pool", "aec_net_finalize",
     "aec_net_destroy", "aec_net_num_layers", "aec_net_num_streams", "aec_net_layer_info",
     "aec_net_state_bytes_per_stream", "aec_net_device_bytes", "aec_net_reset", "aec_net_step_device",
-    "aec_net_step_host", "aec_net_head_device", "aec_net_head_elems_per_stream", "aec_net_begin_step",
+    "aec_net_step_host", "aec_net_head_device", "aec_net_head_elems_per_stream", "aec_net_read_head", "aec_net_begin_step",
     "aec_net_layer_compute", "aec_net_compute_head", "aec_net_read_size", "aec_net_read", "aec_net_read_step_info",
     "aec_net_read_counters", "aec_net_launch_count", "aec_net_read_view", "aec_net_profile", "aec_net_read_profile",
-    "aec_net_count_nonzero_rate_groups", "aec_net_tc_timing", "aec_net_sweep_stats", "aec_net_step_host_async", "aec_net_host_sync", "aec_net_decode_head", "aec_decode_ndata",
+    "aec_net_count_nonzero_rate_groups", "aec_net_tc_timing", "aec_net_tc_geometry", "aec_net_sweep_stats", "aec_net_step_host_async", "aec_net_host_sync", "aec_net_decode_head", "aec_decode_ndata",
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
     L.aec_net_head_device.argtypes = [vp]
     L.aec_net_head_elems_per_stream.restype = sz
     L.aec_net_head_elems_per_stream.argtypes = [vp]
+    L.aec_net_read_head.restype = i
+    L.aec_net_read_head.argtypes = [vp, i, i, vp, vp]
     L.aec_net_begin_step.restype = i
     L.aec_net_begin_step.argtypes = [vp, vp, vp, i, vp]
     L.aec_net_layer_compute.restype = i
@@ -114,6 +116,8 @@ def lib():
     L.aec_net_count_nonzero_rate_groups.argtypes = [vp, ctypes.POINTER(ull), ctypes.POINTER(ull)]
     L.aec_net_tc_timing.restype = i
     L.aec_net_tc_timing.argtypes = [vp, i, i, vp]
+    L.aec_net_tc_geometry.restype = i
+    L.aec_net_tc_geometry.argtypes = [vp, i, vp]
     L.aec_net_sweep_stats.restype = i
     L.aec_net_sweep_stats.argtypes = [vp, vp]
     L.aec_net_launch_count.restype = ull

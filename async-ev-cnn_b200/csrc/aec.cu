@@ -59,6 +59,7 @@ struct HostLayer {
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
     bool tc = false;
     int KB = 0, Mrows = 0, Mch = 0, rep = 1, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
+    bool tc_fast_decode = false;   // which site-decoder variant of k_conv_eval_tc the layer runs (fixed at finalize)
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
@@ -81,6 +82,7 @@ struct aec_net {
     FrontLayer *front_table = nullptr;   // device copy of the per-layer frontier descriptors (k_frontier_all)
     int front_max_words = 0;
     int *counts = nullptr, *err_flag = nullptr;
+    int pending_err = 0, last_err_bits = 0;   // event-error bits latched across an internal sync of the pipelined path
     unsigned long long *accum = nullptr;
     float *head = nullptr;
     size_t head_per_stream = 0;
@@ -97,6 +99,7 @@ struct aec_net {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     unsigned long long async_calls = 0;
     float *head_cur = nullptr;     // where k_head writes (n->head, or a slot's buffer)
+    float *head_last = nullptr;    // where the LAST step wrote the head (aec_net_head_device / aec_net_decode_head read it)
     // CUDA graph of one step (17 launches for EFCN replayed with one call; only the event pointers of the surface kernel and
     // the output pointer of the head kernel change between replays and are patched in place)
     struct StepGraph {
@@ -127,6 +130,7 @@ struct aec_net {
     int prof_slot = 0;
     unsigned long long prof_steps = 0;
     bool tc_timing_on = false;
+    int tc_debug = 0;           // AEC_TC_DEBUG knock-out bits, read once at finalize (measurement only)
     float *view = nullptr;      // 4 x max(H*W*C) scratch for aec_net_read_view
     size_t view_elems = 0;
 };
@@ -458,10 +462,9 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
 
-    static const int dbg = getenv("AEC_TC_DEBUG") ? atoi(getenv("AEC_TC_DEBUG")) : 0;
-    p.debug = dbg;
+    p.debug = n->tc_debug;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
-    if (l.KB >= (getenv("AEC_TC_FASTDEC_KB") ? atoi(getenv("AEC_TC_FASTDEC_KB")) : 10) || (l.m_tiles > 1 && !getenv("AEC_TC_FASTDEC_KB"))) tc::k_conv_eval_tc<true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    if (l.tc_fast_decode) tc::k_conv_eval_tc<true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else tc::k_conv_eval_tc<false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st);
@@ -587,6 +590,7 @@ static HeadParams head_params(aec_net *n, float *out)
 static int run_head(aec_net *n, cudaStream_t st)
 {
     const HeadParams p = head_params(n, n->head_cur ? n->head_cur : n->head);
+    n->head_last = p.out;
     long long total = (long long)n->head_per_stream * n->S;
     int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
     k_head<<<blocks, kThreads, 0, st>>>(p);
@@ -718,6 +722,7 @@ extern "C" int aec_net_finalize(aec_net *n)
 
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
     { const char *e = getenv("AEC_SWEEP_SKIP"); n->sweep_skip = !(e && atoi(e) == 0); }
+    { const char *e = getenv("AEC_TC_DEBUG"); n->tc_debug = e ? atoi(e) : 0; }
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
     int chunk0 = 0, nc = 0;
     for (int pass = 0; pass < 2; ++pass) {
@@ -753,6 +758,10 @@ extern "C" int aec_net_finalize(aec_net *n)
             if (l.type == AEC_LAYER_CONV && l.tc) {
                 tc_max = std::max(tc_max, l.tc_smem);
                 l.tc_blocks = n->num_sms;              // persistent: one warp-specialised CTA per SM (all 512 TMEM columns)
+                // decoder variant per layer (profiles/r1e_summary.md): the batched decoder pays for long units or several
+                // weight tiles; the environment is read here, once, not at every launch
+                const char *fk = getenv("AEC_TC_FASTDEC_KB");
+                l.tc_fast_decode = l.KB >= (fk ? atoi(fk) : 10) || (l.m_tiles > 1 && !fk);
             }
         if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
         if (tc_max) {
@@ -948,6 +957,7 @@ extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t 
                 CU(cudaGraphExecKernelNodeSetParams(g.exec, g.head, &kp));
             }
             CU(cudaGraphLaunch(g.exec, st));
+            n->head_last = out;
             n->launches += g.launches;
             n->steps++;
             return AEC_OK;
@@ -958,9 +968,22 @@ extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t 
     return prof_collect(n, st);
 }
 
-static int upload_events(aec_net *n, const int32_t *ev, const int32_t *off, int total, cudaStream_t st)
+// Host-side check of a packed event batch: offsets start at 0, never decrease and end at `total` - the surface
+// kernel indexes events[off[s] .. off[s+1]) without further checks, and the device buffer is sized from `total`.
+static int check_offsets(const aec_net *n, const int32_t *ev, const int32_t *off, int total)
 {
     if (total < 0 || !off || (total > 0 && !ev)) return fail(AEC_EINVAL, "bad event buffers");
+    if (off[0] != 0) return fail(AEC_EINVAL, "offsets[0] must be 0, got %d", off[0]);
+    for (int s = 0; s < n->S; ++s)
+        if (off[s + 1] < off[s]) return fail(AEC_EINVAL, "offsets decrease at stream %d (%d -> %d)", s, off[s], off[s + 1]);
+    if (off[n->S] != total) return fail(AEC_EINVAL, "offsets[n_streams] = %d does not match total = %d", off[n->S], total);
+    return AEC_OK;
+}
+
+static int upload_events(aec_net *n, const int32_t *ev, const int32_t *off, int total, cudaStream_t st)
+{
+    int rc0 = check_offsets(n, ev, off, total);
+    if (rc0) return rc0;
     if ((size_t)total > n->ev_cap) {
         CU(cudaStreamSynchronize(st));
         if (n->ev_dev) { CU(cudaFree(n->ev_dev)); n->ev_dev = nullptr; }
@@ -978,8 +1001,11 @@ static int check_err_flag(aec_net *n, cudaStream_t st)
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, n->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (flag) CU(cudaMemsetAsync(n->err_flag, 0, sizeof(int), st));
+    flag |= n->pending_err;            // an event error of earlier pipelined steps that no caller has seen yet
+    n->pending_err = 0;
     if (flag) {
-        CU(cudaMemsetAsync(n->err_flag, 0, sizeof(int), st));
+        n->last_err_bits = flag;
         return fail(AEC_EEVENTS, "%s%s", (flag & 1) ? "event coordinates out of range (event skipped). " : "",
                     (flag & 2) ? "a stream exceeded max_events_per_step (stream skipped)." : "");
     }
@@ -1011,7 +1037,7 @@ extern "C" int aec_net_host_sync(aec_net *n, void *cuda_stream)
 extern "C" int aec_net_step_host_async(aec_net *n, const int32_t *ev, const int32_t *off, int total, float *head_out, void *cuda_stream)
 {
     NEED_FINAL(n);
-    if (total < 0 || !off || (total > 0 && !ev)) return fail(AEC_EINVAL, "bad event buffers");
+    { int rc0 = check_offsets(n, ev, off, total); if (rc0) return rc0; }
     if (n->profiling) return fail(AEC_ESTATE, "per-launch profiling is not available on the pipelined host path");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (!n->h2d) {
@@ -1028,7 +1054,8 @@ extern "C" int aec_net_step_host_async(aec_net *n, const int32_t *ev, const int3
         }
         if ((size_t)total > s2.ev_cap) {       // grow the staging buffers: nothing may still be reading them
             int rc = aec_net_host_sync(n, cuda_stream);
-            if (rc && rc != AEC_EEVENTS) return rc;
+            if (rc == AEC_EEVENTS) n->pending_err |= n->last_err_bits;      // reported by the caller's next host_sync
+            else if (rc) return rc;
             if (s2.ev) { CU(cudaFree(s2.ev)); s2.ev = nullptr; }
             const size_t cap = std::max<size_t>((size_t)total * 3 / 2, 1024);
             CU(cudaMalloc(&s2.ev, cap * 3 * sizeof(int32_t)));
@@ -1059,8 +1086,21 @@ extern "C" int aec_net_step_host_async(aec_net *n, const int32_t *ev, const int3
     return AEC_OK;
 }
 
-extern "C" const float *aec_net_head_device(const aec_net *n) { return n ? n->head : nullptr; }
+extern "C" const float *aec_net_head_device(const aec_net *n) { return n ? (n->head_last ? n->head_last : n->head) : nullptr; }
 extern "C" size_t aec_net_head_elems_per_stream(const aec_net *n) { return n ? n->head_per_stream : 0; }
+
+extern "C" int aec_net_read_head(aec_net *n, int first_stream, int count, float *host_out, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    if (first_stream < 0 || count < 0 || first_stream + count > n->S) return fail(AEC_EINVAL, "read_head: streams [%d, %d) out of range", first_stream, first_stream + count);
+    if (count == 0) return AEC_OK;
+    if (!host_out) return fail(AEC_EINVAL, "read_head: host_out is NULL");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float *src = (n->head_last ? n->head_last : n->head) + (size_t)first_stream * n->head_per_stream;
+    CU(cudaMemcpyAsync(host_out, src, (size_t)count * n->head_per_stream * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AEC_OK;
+}
 
 extern "C" int aec_net_begin_step(aec_net *n, const int32_t *ev, const int32_t *off, int total, void *cuda_stream)
 {
@@ -1243,6 +1283,23 @@ extern "C" int aec_net_tc_timing(aec_net *n, int enable, int layer, unsigned lon
     return AEC_OK;
 }
 
+extern "C" int aec_net_tc_geometry(const aec_net *n, int layer, long long *out8)
+{
+    if (!n || !out8 || layer < 0 || layer >= (int)n->L.size()) return fail(AEC_EINVAL, "tc_geometry: bad layer index %d", layer);
+    const HostLayer &l = n->L[layer];
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (l.type != AEC_LAYER_CONV || !l.tc) return AEC_OK;
+    const long long k8 = (l.K + 7) / 8;
+    out8[0] = 1;
+    out8[1] = tc::kUnitSites;
+    out8[4] = 3;                                                   // W_hi.X_lo + W_lo.X_hi + W_hi.X_hi
+    out8[5] = l.m_tiles;
+    out8[3] = k8;
+    out8[2] = k8 * out8[4] * l.m_tiles * 2LL * 128 * tc::kUnitCols * 8;   // every MMA is M128 x N256 x K8
+    out8[6] = l.tc_fast_decode ? 1 : 0;
+    return AEC_OK;
+}
+
 extern "C" int aec_net_sweep_stats(aec_net *n, unsigned long long *out8)
 {
     NEED_FINAL(n);
@@ -1298,7 +1355,7 @@ extern "C" int aec_net_decode_head(aec_net *n, int num_classes, int num_bbox, in
         n->dec_cap = nb;
     }
     DecodeParams p;
-    p.head = n->head; p.boxes = n->dec_boxes; p.conf = n->dec_conf; p.label = n->dec_label; p.valid = n->dec_valid;
+    p.head = n->head_last ? n->head_last : n->head; p.boxes = n->dec_boxes; p.conf = n->dec_conf; p.label = n->dec_label; p.valid = n->dec_valid;
     p.S = n->S; p.gh = h_cells; p.gw = w_cells; p.C = num_classes; p.B = num_bbox; p.h_img = h_image; p.w_img = w_image;
     p.thr = conf_threshold;
     const int blocks = (int)std::min<size_t>((nb + kThreads - 1) / kThreads, (size_t)n->num_sms * 8);

@@ -104,6 +104,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 24)) __trap();
 }
+// Warp-level forms.  An mbarrier arrive is a shared-memory atomic per executing LANE and a try_wait a shared-memory
+// read per lane; with every thread of a role arriving and polling, those came to 42 % of the kernel's LSU
+// shared-memory wavefronts (profiles/r2a: 28 M arrive + 38 M poll wavefronts against 98 M of real operand traffic
+// per conv2 launch), on a kernel bounded by shared-memory bandwidth.  So one lane per warp polls / arrives for the
+// warp: __syncwarp orders the other lanes' accesses with it (barrier counts are per warp accordingly).
+__device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_arrive(uint32_t bar)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -211,6 +226,17 @@ __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool o
         acc += clock64() - t0;
     } else {
         mbar_wait(bar, parity);
+    }
+}
+// the same for a whole (converged) warp: lane 0 polls
+__device__ __forceinline__ void timed_warp_wait(uint32_t bar, uint32_t parity, bool on, long long &acc)
+{
+    if (on) {
+        const long long t0 = clock64();
+        warp_wait(bar, parity);
+        acc += clock64() - t0;
+    } else {
+        warp_wait(bar, parity);
     }
 }
 
@@ -338,7 +364,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
 
     if (tid == 0) {
         for (int i = 0; i < kSiteStages; ++i) {
-            mbar_init(smem_u32(&bar_x_full[i]), 2 * kGroupThreads);      // both halves of the stage (two producer groups)
+            mbar_init(smem_u32(&bar_x_full[i]), 2 * kGroupThreads / 32); // both halves of the stage (two producer groups), one arrival per warp
             mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
         for (int i = 0; i < p.w_stages; ++i) {
@@ -347,11 +373,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bar_acc_full[i]), 1);
-            mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps * 32);
+            mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps);           // one arrival per epilogue warp
         }
         for (int i = 0; i < kSiteRing; ++i) {
             mbar_init(smem_u32(&bar_si_full[i]), 1);
-            mbar_init(smem_u32(&bar_si_free[i]), kEpiWarps * 32);
+            mbar_init(smem_u32(&bar_si_free[i]), kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -382,8 +408,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const int mg = unit % n_mgroups;
             const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
             const int buf = ul % kSiteRing, ab = ul % p.n_acc;
-            timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul / kSiteRing) & 1u, timing, tw_si);
-            timed_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u, timing, tw_acc);
+            timed_warp_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul / kSiteRing) & 1u, timing, tw_si);
+            timed_warp_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u, timing, tw_acc);
             tc_fence_after();
             if (warp_live) {
                 for (int mt = 0; mt < mt_count; ++mt) {
@@ -425,8 +451,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 }
             }
             tc_fence_before();
-            mbar_arrive(smem_u32(&bar_acc_empty[ab]));
-            mbar_arrive(smem_u32(&bar_si_free[buf]));
+            warp_arrive(smem_u32(&bar_acc_empty[ab]));
+            warp_arrive(smem_u32(&bar_si_free[buf]));
         }
         if (timing && tid == 0) {
             atomicAdd(p.timing + kTEpiTotal, (unsigned long long)(clock64() - t_begin));
@@ -504,7 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
             const int ab = ul % p.n_acc;
             const uint32_t ua = (uint32_t)(ul / p.n_acc);
-            if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
+            if (ua > 0) timed_warp_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
                 const uint32_t sx = qx % (uint32_t)kSiteStages;
                 const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
@@ -512,8 +538,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
                     // every wait costs ~170 cycles even when the barrier is already complete: the weights (normally early)
                     // first, the site stage (normally the last thing to arrive) last, one barrier for both of its halves
-                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
-                    if (mt == 0) timed_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
+                    timed_warp_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                    if (mt == 0) timed_warp_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
                     asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qw & 3u)) : "memory");
                 }
             }
@@ -572,7 +598,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     const long long gi = (long long)blk * kUnitSites + lane + 32 * k;
                     ent[k] = gi < n_sites ? __ldg(p.sites + gi) : 0xffffffffu;
                 }
-                if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
+                if (us > 0) warp_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
     #pragma unroll
                 for (int k = 0; k < kUnitSites / 32; ++k) {
                     const int i = lane + 32 * k;
@@ -599,7 +625,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     s_dst[buf][i] = dst;
                 }
             } else {
-                if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
+                if (us > 0) warp_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
                 for (int i = lane; i < kUnitSites; i += 32) {
                     const long long gi = (long long)blk * kUnitSites + i;
                     SiteSrc q;
@@ -647,7 +673,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         auto load = [&](const Pos &c, float4 (&f)[kPairs], float4 (&a)[kPairs]) {
             const int buf = c.ul % kSiteRing;
             if (c.ul > ready_ul) {
-                timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(c.ul / kSiteRing) & 1u, timing, tw_si);
+                timed_warp_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(c.ul / kSiteRing) & 1u, timing, tw_si);
                 ready_ul = c.ul;
             }
             const KEntry e = c.kb < kKtabBlocks ? s_ktab[c.kb * 8 + (t & 7)] : make_kentry(p, c.kb, t & 7);
@@ -657,11 +683,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         auto store = [&](const Pos &c, const float4 (&f)[kPairs], const float4 (&a)[kPairs]) {
             const uint32_t qx = c.q >> 1;
             const uint32_t sx = qx % (uint32_t)kSiteStages, use = qx / (uint32_t)kSiteStages;
-            if (use > 0) timed_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
+            if (use > 0) timed_warp_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
             const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes + (uint32_t)c.h * (uint32_t)kItemTileBytes;
             item_store(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
             fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
-            mbar_arrive(smem_u32(&bar_x_full[sx]));
+            warp_arrive(smem_u32(&bar_x_full[sx]));
         };
         Pos cur;
         cur.q = (uint32_t)g; cur.ul = 0; cur.kb = g >> 1; cur.h = g & 1;

@@ -119,8 +119,20 @@ class EventNetCuda:
 
     # -- stepping -----------------------------------------------------------------------------
     def reset(self, stream_mask=None, cuda_stream=None):
-        m = None if stream_mask is None else np.ascontiguousarray(stream_mask, dtype=np.uint8)
+        """Back to the initial state (conv2d.py:99-103, maxpool.py:84-90, integration.py:48-51): every stream, or the
+        streams whose entry of `stream_mask` (length n_streams) is non-zero."""
+        m = None
+        if stream_mask is not None:
+            m = np.ascontiguousarray(stream_mask, dtype=np.uint8)
+            if m.shape != (self.n_streams,):        # the library copies n_streams bytes from this pointer
+                raise ValueError("reset mask must have shape (%d,), got %s" % (self.n_streams, m.shape))
         N.check(self._lib.aec_net_reset(self._h, _ptr(m), cuda_stream))
+
+    def _check_out(self, out):
+        want = (self.n_streams,) + self.head_shape
+        if not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != want:
+            raise ValueError("`out` must be a C-contiguous float32 array of shape %s" % (want,))
+        return out
 
     def _raise_events(self, err):
         if err.code == N.AEC_EEVENTS:
@@ -131,8 +143,9 @@ class EventNetCuda:
         """Host->device->host step: events int32 [total,3], offsets int32 [S+1] -> head [S,H,W,C] float32."""
         events = np.ascontiguousarray(events, dtype=np.int32)
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
-        assert offsets.shape == (self.n_streams + 1,)
-        out = self._head if out is None else out
+        if offsets.shape != (self.n_streams + 1,):
+            raise ValueError("offsets must have shape (%d,), got %s" % (self.n_streams + 1, offsets.shape))
+        out = self._head if out is None else self._check_out(out)
         try:
             N.check(self._lib.aec_net_step_host(self._h, _ptr(events), _ptr(offsets), int(offsets[-1]), _ptr(out), cuda_stream))
         except N.AecError as e:
@@ -142,8 +155,11 @@ class EventNetCuda:
     def step_packed_async(self, events, offsets, out, cuda_stream=None):
         """Pipelined host step (aec_net_step_host_async): returns once enqueued.  `events`, `offsets`, `out` must be
         C-contiguous int32 / int32 / float32 arrays (pinned for real overlap) that stay untouched until host_sync()."""
-        assert events.dtype == np.int32 and offsets.dtype == np.int32 and out.dtype == np.float32
-        assert events.flags.c_contiguous and offsets.flags.c_contiguous and out.flags.c_contiguous
+        if events.dtype != np.int32 or offsets.dtype != np.int32 or not events.flags.c_contiguous or not offsets.flags.c_contiguous:
+            raise ValueError("events / offsets must be C-contiguous int32 arrays")
+        if offsets.shape != (self.n_streams + 1,):
+            raise ValueError("offsets must have shape (%d,), got %s" % (self.n_streams + 1, offsets.shape))
+        self._check_out(out)
         N.check(self._lib.aec_net_step_host_async(self._h, _ptr(events), _ptr(offsets), int(offsets[-1]), _ptr(out), cuda_stream))
 
     def host_sync(self, cuda_stream=None):
@@ -179,6 +195,13 @@ class EventNetCuda:
 
     def head_device_ptr(self):
         return int(self._lib.aec_net_head_device(self._h))
+
+    def read_head(self, first_stream=0, n=None, cuda_stream=None):
+        """Host copy of the last step's head for streams [first_stream, first_stream + n) (after step_device)."""
+        n = self.n_streams - first_stream if n is None else int(n)
+        out = np.empty((n,) + self.head_shape, np.float32)
+        N.check(self._lib.aec_net_read_head(self._h, int(first_stream), n, _ptr(out), cuda_stream))
+        return out
 
     def begin_step(self, per_stream_events):
         if isinstance(per_stream_events, np.ndarray) and per_stream_events.ndim == 2:
@@ -297,6 +320,16 @@ class EventNetCuda:
             if info.type == N.AEC_LAYER_CONV and i > 1 and info.in_channels % 4 == 0 and info.k_h * info.k_w <= 32:
                 out.append(i)
         return out
+
+    def tc_geometry(self, layer):
+        """How conv layer `layer` maps onto the tensor cores (aec_net_tc_geometry), or None for a SIMT layer."""
+        buf = np.zeros(8, np.int64)
+        N.check(self._lib.aec_net_tc_geometry(self._h, int(layer), _ptr(buf)))
+        if not buf[0]:
+            return None
+        return {"unit_sites": int(buf[1]), "mma_flops_per_unit": float(buf[2]), "m_groups": 1, "k8_steps": int(buf[3]),
+                "mma_per_kstep": int(buf[4]), "weight_tiles": int(buf[5]),
+                "kernel": "k_conv_eval_tc<%d>" % int(buf[6])}
 
     TC_TIMING_SLOTS = ("mma_total", "mma_wait_acc", "mma_wait_sites", "mma_wait_weights", "prod_total", "prod_wait_siteinfo",
                        "prod_wait_stage", "epi_total", "epi_wait_acc", "epi_wait_siteinfo", "load_total", "load_wait", "ctas", "units",

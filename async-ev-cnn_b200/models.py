@@ -100,12 +100,17 @@ class YoloEventCuda:
                 if reset:
                     net.reset()
                 return np.reshape(net.step([input])[0], out_shape).copy()
-            if np.any(reset):
-                net.reset(None if reset is True else np.asarray(reset, np.uint8))
+            if np.ndim(reset) == 0:                                  # True / np.True_ / 1: every stream
+                if bool(reset):
+                    net.reset()
+            elif np.any(reset):
+                net.reset(np.asarray(reset, np.uint8))               # per-stream mask, length checked by the engine
             if isinstance(input, tuple):
                 heads = net.step_packed(*input)
             else:
                 heads = net.step_packed(*pack_events(input))
-            return np.reshape(heads, [S] + out_shape)
+            # a fresh array per call: the engine reuses its head buffer, and callers keep results across steps
+            # (runner.py:100 appends net_out to a list)
+            return np.reshape(heads, [S] + out_shape).copy()
 
         return graph

@@ -83,6 +83,89 @@ def gather_detections(local_heads, n_streams, group=None, dst=0):
     return None
 
 
+class SharedHostGather:
+    """Detections of all ranks of ONE box assembled in one host array without a staging copy.
+
+    Rank `dst` creates a POSIX shared-memory segment holding `slots` arrays [n_streams, *tail] float32; every rank
+    maps it and owns the rows of its stream block (`mine(slot)`).  On a GPU box each rank page-locks its mapping
+    (cudaHostRegister), so its device-to-host copy of the head lands directly in the assembled array over the GPU's
+    own PCIe link: "detections are gathered on the host" (north_star) costs no extra pass and no collective.  After
+    `complete()` (a barrier of the group) rank `dst` may read `assembled(slot)`.  Under gloo on CPU the same object
+    works unpinned (tests/test_sharding.py).  Multi-node groups must use gather_detections instead."""
+
+    def __init__(self, n_streams, tail, slots=2, group=None, dst=0, pin=None):
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.group, self.dst, self.slots = group, dst, int(slots)
+        self.n_streams, self.tail = int(n_streams), tuple(int(t) for t in tail)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lo, self.hi = shard_bounds(self.n_streams, self.world, self.rank)
+        nbytes = max(1, self.slots * self.n_streams * int(np.prod(self.tail)) * 4)
+        name = [None]
+        if self.rank == dst:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self._shm.name
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=dst, group=group)
+        if self.rank != dst:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:                                       # the creator unlinks the segment; attached ranks must not
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.buf = np.ndarray((self.slots, self.n_streams) + self.tail, np.float32, buffer=self._shm.buf)
+        self._pinned = False
+        if pin is None:
+            try:
+                import torch
+                pin = torch.cuda.is_available()
+            except Exception:
+                pin = False
+        if pin:
+            import torch
+            rc = torch.cuda.cudart().cudaHostRegister(self.buf.ctypes.data, self.buf.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister of the shared detection buffer failed: %s" % rc)
+            self._pinned = True
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def mine(self, slot):
+        """This rank's rows of slot `slot` (a writable view: the D2H target of the rank's head)."""
+        return self.buf[slot % self.slots, self.lo:self.hi]
+
+    def complete(self):
+        """Every rank has finished writing its rows (call after the rank's own copies are done)."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def assembled(self, slot):
+        """[n_streams, *tail] view on rank `dst` (None elsewhere); valid after complete()."""
+        return self.buf[slot % self.slots] if self.rank == self.dst else None
+
+    def close(self):
+        if self._shm is None:
+            return
+        if self._pinned:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.buf.ctypes.data)
+            self._pinned = False
+        self.buf = None
+        shm, self._shm = self._shm, None
+        shm.close()
+        if self.rank == self.dst:
+            shm.unlink()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedEventNet:
     """`n_streams` GLOBAL streams spread over the ranks of the current process group, one
     EventNetCuda per rank on GPU `device` (default: LOCAL_RANK).  step() takes the GLOBAL per-stream
@@ -106,6 +189,7 @@ class ShardedEventNet:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.net = EventNetCuda(height, width, layers, weights, leak, alpha, padding, n_streams=self.hi - self.lo,
                                 device=device, max_events_per_step=max_events_per_step)
+        self.gather = None
 
     def reset(self, reset=True):
         m = shard_reset_mask(reset, self.n_streams, self.world, self.rank)
@@ -121,5 +205,32 @@ class ShardedEventNet:
         heads = self.net.step(per_stream_events[self.lo:self.hi])
         return gather_detections(heads, self.n_streams, self.group)
 
+    # -- pipelined form: packed local events in, detections assembled in host shared memory (one box) ------------
+    def open_host_gather(self, slots=2):
+        """Creates the shared, page-locked detection buffer (collective: every rank must call it)."""
+        self.gather = SharedHostGather(self.n_streams, self.net.head_shape, slots=slots, group=self.group)
+        self._slot = 0
+        return self.gather
+
+    def step_packed_async(self, events, offsets, cuda_stream=None):
+        """This rank's packed events (int32 [total,3], int32 [S_rank+1], pinned for real overlap) -> the step is
+        enqueued and its head is copied straight into this rank's rows of the next shared slot.  Returns the slot."""
+        slot = self._slot
+        self.net.step_packed_async(events, offsets, self.gather.mine(slot), cuda_stream=cuda_stream)
+        self._slot = (slot + 1) % self.gather.slots
+        return slot
+
+    def sync(self, cuda_stream=None):
+        """Waits for this rank's enqueued steps and for every other rank's: afterwards rank 0 may read
+        `assembled(slot)` = [n_streams, H, W, C] of the steps enqueued so far."""
+        self.net.host_sync(cuda_stream)
+        self.gather.complete()
+
+    def assembled(self, slot):
+        return self.gather.assembled(slot)
+
     def close(self):
+        if getattr(self, "gather", None) is not None:
+            self.gather.close()
+            self.gather = None
         self.net.close()

@@ -15,13 +15,25 @@ that collected a few events stays alive for 40-100 steps (1/leak = 20 ms = 40 st
 surface value), so the live-site fraction and the frontier sizes settle only after ~120 steps
 (tools/diag_sustained2.py); the default pre-roll is 160 steps, on the GPU and in the CPU arms alike.
 
-One JSON line is printed by rank 0 (see the keys at the bottom).  Nothing here reads /root/reference.
+What the one JSON line holds beyond the contract keys:
+  parity_check   the CPU baseline's streams ARE GPU streams 0..P-1 (same events); after the pre-roll the oracle's
+                 head / frontier sets / pool argmax / flags of those streams are compared with the GPU's
+  roofline       dominant kernel (gathered GEMM on the tensor cores) + a per-layer table of every launch of the step
+  roofline_hbm   the leak sweep and the whole step in algorithmic bytes
+  legs           BASELINE configs 4 and 5 measured in the same run (K = 5 each): uniform streams, 256 and 4096
+                 streams per GPU, and the DAVIS346-sized stress net (256x320, deeper EFCN, 1000 / 2000 events/step)
+  e2e            through ShardedEventNet (the multi-GPU product path): pinned host events in, every rank's head
+                 copied straight into one shared page-locked host array -> [n_gpus*S, 5, 7, 110] assembled on rank 0
+
+Nothing here reads /root/reference.
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -34,6 +46,12 @@ if ROOT not in sys.path:
 H, W, LEAK, ALPHA = 160, 224, 5e-5, 0.1
 METRIC = "efcn_event_inference_throughput"
 UNIT = "events/s"
+# BASELINE config 5 ("deeper EFCN variant", builder-defined as SURVEY 8(d) allows: two 3x3 convs in the first two
+# stages), on a DAVIS346 frame cropped to 256x320 (pooled dimensions must be even)
+STRESS_LAYERS = ("conv1=3,3,1,16 conv1b=3,3,16,16 pool1=2,2 conv2=3,3,16,32 conv2b=3,3,32,32 pool2=2,2 conv3=3,3,32,64 pool3=2,2 "
+                 "conv4=3,3,64,128 pool4=2,2 conv5=3,3,128,256 pool5=2,2 conv6=1,1,256,512 conv7=1,1,512,110")
+STRESS_H, STRESS_W, STRESS_RATE = 256, 320, 10.0        # 10 events/us = 10 Mev/s per stream
+CPU_MAX_STEPS = 600                                      # timed CPU steps available to a baseline worker
 
 
 def parse_args():
@@ -47,11 +65,15 @@ def parse_args():
     ap.add_argument("--kind", default="edge", choices=["edge", "uniform"], help="synthetic stream kind (SURVEY 8d)")
     ap.add_argument("--preroll", type=int, default=160, help="untimed steps to reach the workload's steady state (live-site fraction settles after ~120)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the BASELINE config 4 / 5 legs (they run at --gpus 1 only)")
+    ap.add_argument("--leg-steps", type=int, default=5)
     ap.add_argument("--latency-steps", type=int, default=100, help="steps of the single-stream latency measurement (0 = skip)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="extra back-to-back steps after the timed region (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="timed CPU work per core for the baseline")
     ap.add_argument("--cpu-worker", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-steps", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-events", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-dump", default=None, help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -60,23 +82,35 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 def cpu_worker(args):
     """One process = one stream on one core, OMP_NUM_THREADS=1.  Times only the
-    compute chain + final featuremap, as runner.py:84-89 does for the event runner."""
+    compute chain + final featuremap, as runner.py:84-89 does for the event runner.  The stream is row
+    `--cpu-worker` of the event file the parent wrote (the same events GPU stream `--cpu-worker` gets); with
+    --cpu-dump the integer state and the head after the untimed steps are saved for the parity check."""
     import async_ev_cnn_b200 as P
     from oracle.event_oracle import OracleEventNet
-    seed = args.cpu_worker
+    idx = args.cpu_worker
     wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
     net = OracleEventNet(H, W, P.EFCN_LAYERS, wts, LEAK, ALPHA, "SAME")
-    max_steps = args.cpu_steps if args.cpu_steps > 0 else 2000
-    n_steps = args.preroll + args.warmup + max_steps
-    evs = P.synthetic_events(args.kind, 1, n_steps, args.batch, H, W, seed=1000 + seed)[0]
+    evs = np.load(args.cpu_events, mmap_mode="r")[idx]
+    untimed = args.preroll + args.warmup
+    max_steps = args.cpu_steps if args.cpu_steps > 0 else evs.shape[0] - untimed
     t = 0
-    for _ in range(args.preroll + args.warmup):
-        net.step(evs[t])
+    head = None
+    for _ in range(untimed):
+        head = net.step(np.asarray(evs[t]))
         t += 1
+    if args.cpu_dump:
+        rec = {"head": np.asarray(head, np.float32)}
+        for i, nm in enumerate(net.names):
+            rec["front_" + nm] = np.packbits(net.frontier_mask(i))
+            layer = net.layers[i]
+            if hasattr(layer, "idx"):
+                rec["idx_" + nm] = layer.idx.reshape(layer.shape).astype(np.uint8)
+                rec["flags_" + nm] = np.packbits(layer.flags)
+        np.savez(args.cpu_dump + "%d.npz" % idx, **rec)
     done = 0
     t0 = time.perf_counter()
     while done < max_steps:
-        net.step(evs[t])
+        net.step(np.asarray(evs[t]))
         t += 1
         done += 1
         if args.cpu_steps <= 0 and time.perf_counter() - t0 >= args.cpu_seconds:
@@ -85,15 +119,21 @@ def cpu_worker(args):
     print(json.dumps({"steps": done, "seconds": dt}))
 
 
-def run_cpu_processes(args, fixed_steps):
-    """Runs one worker per host core concurrently; returns (aggregate events/s, cores, per-core steps, seconds)."""
-    cores = os.cpu_count() or 1
+def check_streams(args, P, n_check, untimed, timed):
+    """Events of the streams that both the CPU workers and GPU streams 0..n_check-1 consume: [n_check, steps, B, 3]."""
+    return P.synthetic_events(args.kind, n_check, untimed + timed, args.batch, H, W, seed=7000)
+
+
+def run_cpu_processes(args, fixed_steps, events_path, warmup, cores, dump_prefix=None):
+    """Runs `cores` workers (one per host core) concurrently; returns (aggregate events/s, cores, per-core steps, seconds)."""
     env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     cmd = [sys.executable, os.path.abspath(__file__), "--kind", args.kind, "--batch", str(args.batch),
-           "--preroll", str(args.preroll), "--warmup", str(max(args.warmup, 2)), "--cpu-seconds", str(args.cpu_seconds),
-           "--cpu-steps", str(fixed_steps)]
+           "--preroll", str(args.preroll), "--warmup", str(warmup), "--cpu-seconds", str(args.cpu_seconds),
+           "--cpu-steps", str(fixed_steps), "--cpu-events", events_path]
+    if dump_prefix:
+        cmd += ["--cpu-dump", dump_prefix]
     procs = [subprocess.Popen(cmd + ["--cpu-worker", str(i)], stdout=subprocess.PIPE, env=env, text=True) for i in range(cores)]
     rate, steps, secs = 0.0, [], []
     for p in procs:
@@ -112,16 +152,25 @@ def reference_arm(args):
     The reference is Python + one Cython module and cannot travel to the GPU box, so this times the
     oracle port (bit-identical to the reference and equally fast: tests/test_oracle_vs_reference.py),
     one stream per core on all cores; a step = every core advances its stream by one batch."""
+    import async_ev_cnn_b200 as P
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, args.steps)
-    rate, cores, st, secs = run_cpu_processes(args, fixed_steps=steps)
+    warm = max(args.warmup, 2)
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="aec_bench_")
+    try:
+        path = os.path.join(tmp, "events.npy")
+        np.save(path, check_streams(args, P, cores, args.preroll + warm, steps))
+        rate, cores, st, secs = run_cpu_processes(args, steps, path, warm, cores)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     ms = 1e3 * float(np.mean(secs)) / steps
     sample = "%d cores x 1 stream x %d steps x %d events (%s stream, %d pre-roll steps)" % (cores, steps, args.batch, args.kind, args.preroll)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.streams),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -176,43 +225,202 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# GPU side
+# GPU side: accounting
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(net, sites_per_step, sw, streams, batch):
+def layer_bytes(net, i, n, streams):
+    """Algorithmic bytes of layer i's evaluation for n re-evaluated sites / windows: a conv writes F and A
+    at its sites (8 B x Cout) and reads every distinct input value + rate once (8 B x Cin, at most the whole input
+    map); a pool reads 4 values + 4 rates and writes the index per (window, channel) (36 B)."""
+    shapes = net.shapes()
+    c, h, w = shapes[i]
+    nm = net.names[i]
+    if "conv" in nm:
+        cin, hin, win = shapes[i - 1]
+        k = net.infos[i].k_h * net.infos[i].k_w
+        in_bytes = 8 * cin if i > 1 else 8            # first conv reads the float64 surface
+        return n * 8 * c + min(k * n, streams * hin * win) * in_bytes
+    if "pool" in nm:
+        return n * c * 36.0
+    return 0.0
+
+
+def algorithmic_bytes(net, sites_per_step, sw, streams, batch, h, w):
     """SURVEY 8(d) / BASELINE.md section 4 per step over all streams, with the leak term stated for what the
     implemented algorithm needs: A and F are read and F written (12 B/elem) at the live sites (non-zero-rate bit
     set) that the step does not re-evaluate anyway - a re-evaluated site gets F and A overwritten, so its leak is
     not needed (`swept_conv_elems`) - plus the bitmaps (non-zero-rate, skip, sign-change).
     The pool layers' (Fp, Ap) copies are an implementation choice and are NOT counted as algorithmic."""
     shapes = net.shapes()
-    nz4 = sw["nz_groups"] / max(1, sw["groups"])
-    bitmaps = sum(h * ((w + 31) // 32) * 4 for nm, (c, h, w) in zip(net.names, shapes) if "conv" in nm) * streams
+    bitmaps = sum(hh * ((ww + 31) // 32) * 4 for nm, (c, hh, ww) in zip(net.names, shapes) if "conv" in nm) * streams
     leak = 12.0 * sw.get("swept_conv_elems", sw["live_conv_elems"]) + 3 * bitmaps
-    surface = streams * 2 * 8 * H * W
+    surface = streams * 2 * 8 * h * w
     ev = streams * 12 * batch
-    conv = pool = 0.0
-    for i, nm in enumerate(net.names):
-        c, h, w = shapes[i]
-        n = float(sites_per_step[i])
-        if "conv" in nm:
-            cin, hin, win = shapes[i - 1]
-            k = net.infos[i].k_h * net.infos[i].k_w
-            conv += n * 8 * c + min(k * n, streams * hin * win) * 8 * cin
-        elif "pool" in nm:
-            pool += n * c * 36
-    leak_dense = 12.0 * sw["conv_elems"]          # SURVEY 8(d) as written: the reference's dense leak pass, 12 B per conv element
+    conv = sum(layer_bytes(net, i, float(sites_per_step[i]), streams) for i, nm in enumerate(net.names) if "conv" in nm)
+    pool = sum(layer_bytes(net, i, float(sites_per_step[i]), streams) for i, nm in enumerate(net.names) if "pool" in nm)
     return {"leak_sweep": leak, "surface": surface, "conv": conv, "pool": pool, "events": ev,
-            "total": leak + surface + conv + pool + ev, "total_survey_8d": leak_dense + surface + conv + pool + ev}
+            "total": leak + surface + conv + pool + ev}
 
 
-def conv_flops(net, sites_per_step, layers):
-    """Useful FLOPs per step of the gathered GEMM over `layers`: sites x {value, rate} x 2 x K x Cout."""
-    shapes = net.shapes()
-    fl = 0.0
-    for i in layers:
-        info = net.infos[i]
-        fl += float(sites_per_step[i]) * 2 * 2 * info.k_h * info.k_w * info.in_channels * shapes[i][0]
-    return fl
+def layer_flops(net, i, n):
+    """Useful FLOPs of conv layer i for n re-evaluated sites: sites x {value, rate} x 2 x K x Cout."""
+    info = net.infos[i]
+    return float(n) * 2 * 2 * info.k_h * info.k_w * info.in_channels * net.shapes()[i][0]
+
+
+def tf32_peak(peaks, sm_mhz):
+    """Measured tensor peak for kind::tf32: profiles/r2_umma_peak.json holds the cycles one tcgen05.mma
+    (M128 x N256 x K8) takes when issued back to back (tools/bench_umma.cu, run on the box); x 148 SMs x the SM clock
+    sampled during the timed region.  Fallback: MEASURED_PEAKS bf16 sustained / 2."""
+    try:
+        um = json.load(open(os.path.join(ROOT, "profiles", "r2_umma_peak.json")))
+        cyc = float(um["tf32_m128_n256_k8_cycles_per_mma"])
+        mhz = float(sm_mhz or um.get("sm_mhz_assumed", 1800.0))
+        sms = int(um.get("sms", 148))
+        return 2.0 * 128 * 256 * 8 / cyc * sms * mhz * 1e6 / 1e12, "profiles/r2_umma_peak.json: %.1f cycles per M128xN256xK8 kind::tf32 MMA (tools/bench_umma.cu on the box) x %d SMs x %.0f MHz (SM clock sampled in the timed region)" % (cyc, sms, mhz)
+    except Exception:
+        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        return bf16 / 2.0, ("MEASURED_PEAKS.json bf16_tflops_sustained / 2" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s bf16 / 2")
+
+
+def layer_table(net, prof, sites_per_step, streams, tf32_pk, hbm_pk):
+    """Per-launch table of one step: ms, work, useful TFLOP/s (conv) and algorithmic GB/s against the measured peaks."""
+    rows = {}
+    for i, nm in enumerate(net.names):
+        if i == 0:
+            continue
+        ms = prof.get(nm + ".eval", 0.0)
+        n = float(sites_per_step[i])
+        row = {"ms": round(ms, 4), "sites_per_stream": round(n / streams, 1)}
+        b = layer_bytes(net, i, n, streams)
+        if ms > 0:
+            row["alg_GB"] = round(b / 1e9, 4)
+            row["alg_GBps"] = round(b / (ms * 1e-3) / 1e9, 1)
+            row["hbm_frac"] = round(b / (ms * 1e-3) / 1e9 / hbm_pk, 4)
+            if "conv" in nm:
+                fl = layer_flops(net, i, n)
+                tc = net.tc_geometry(i)
+                row["useful_TFLOPs"] = round(fl / (ms * 1e-3) / 1e12, 2)
+                row["useful_frac_of_tf32_peak"] = round(fl / (ms * 1e-3) / 1e12 / tf32_pk, 4)
+                if tc is not None:
+                    issued = tc["mma_flops_per_unit"] * np.ceil(n / tc["unit_sites"]) * tc["m_groups"]
+                    row["issued_TFLOPs"] = round(issued / (ms * 1e-3) / 1e12, 2)
+                    row["issued_frac_of_tf32_peak"] = round(issued / (ms * 1e-3) / 1e12 / tf32_pk, 4)
+                    row["kernel"] = tc["kernel"]
+                else:
+                    row["kernel"] = "k_conv_stencil / k_conv_eval (SIMT)"
+            else:
+                row["kernel"] = "k_pool_eval"
+        rows[nm] = row
+    return rows
+
+
+def gen_events(P, kind, S, n_steps, B, h, w, seed, rate=0.4, block=256):
+    """[n_steps, S*B, 3] int32, streams packed per step; generated in blocks of streams to bound the temporaries."""
+    out = np.empty((n_steps, S * B, 3), np.int32)
+    for b0 in range(0, S, block):
+        nb = min(block, S - b0)
+        ev = P.synthetic_events(kind, nb, n_steps, B, h, w, seed=seed + 7919 * (b0 // block), rate=rate)
+        out[:, b0 * B:(b0 + nb) * B] = ev.transpose(1, 0, 2, 3).reshape(n_steps, nb * B, 3)
+    return out
+
+
+def run_leg(torch, P, EventNetCuda, name, layers, h, w, S, B, kind, preroll, K, local, peaks, rate=0.4, seed=300):
+    """One extra configuration measured like the headline: pre-roll on device-resident events, K timed steps between
+    CUDA events, then K profiled steps for the per-launch table."""
+    wts = P.xavier_weights(layers, seed=0 if layers == P.EFCN_LAYERS else 3)
+    n_steps = preroll + 3 + 2 * K
+    t_gen = time.perf_counter()
+    ev_np = gen_events(P, kind, S, n_steps, B, h, w, seed, rate=rate)
+    t_gen = time.perf_counter() - t_gen
+    net = EventNetCuda(h, w, layers, wts, LEAK, ALPHA, "SAME", n_streams=S, device=local, max_events_per_step=max(2048, B))
+    ev_dev = torch.from_numpy(ev_np).cuda()
+    off_dev = torch.from_numpy((np.arange(S + 1, dtype=np.int64) * B).astype(np.int32)).cuda()
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    t = 0
+    for _ in range(preroll + 3):
+        net.step_device(ev_dev[t].data_ptr(), off_dev.data_ptr(), S * B, sh)
+        t += 1
+    net.counters(reset=True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    time.sleep(0.2)
+    w0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        net.step_device(ev_dev[t].data_ptr(), off_dev.data_ptr(), S * B, sh)
+        t += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop(w0, time.perf_counter())
+    ms = e0.elapsed_time(e1) / K
+    sites, _ = net.counters(reset=True)
+    sites_per_step = sites.astype(np.float64) / K
+    sw = net.sweep_stats()
+    net.profile(True)
+    for _ in range(K):
+        net.step_device(ev_dev[t].data_ptr(), off_dev.data_ptr(), S * B, sh)
+        t += 1
+    prof, _ = net.read_profile()
+    net.profile(False)
+    hbm_pk = float(peaks.get("hbm_gbs", 6650.0))
+    tf_pk, _ = tf32_peak(peaks, clocks.get("sm_mhz"))
+    ab = algorithmic_bytes(net, sites_per_step, sw, S, B, h, w)
+    table = layer_table(net, prof, sites_per_step, S, tf_pk, hbm_pk)
+    top = max(prof.items(), key=lambda kv: kv[1])
+    out = {"value": S * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "preroll_steps": preroll,
+           "streams_per_gpu": S, "batch_event_size": B, "stream_kind": kind, "frame": [h, w], "event_rate_per_us": rate,
+           "state_GB": round(net.device_bytes() / 1e9, 2),
+           "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": ab["total"] / (ms * 1e-3) / 1e9 / hbm_pk},
+           "dominant_launch": {"name": top[0], "ms": round(top[1], 4), "share": round(top[1] / max(1e-9, sum(prof.values())), 3)},
+           "ms_by_launch": {k: round(v, 4) for k, v in prof.items()}, "layers": table,
+           "live_site_fraction": sw["live_conv_elems"] / max(1, sw["conv_elems"]),
+           "clocks": clocks, "host_seconds_generating_events": round(t_gen, 1)}
+    net.close()
+    del ev_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def parity_check(net, dump_prefix, n_check, steps_done):
+    """GPU streams 0..n_check-1 against the oracle workers that consumed the same events, after `steps_done` steps."""
+    heads = net.read_head(0, n_check)
+    out = {"streams": n_check, "steps": steps_done, "head_max_rel_err": 0.0, "frontier_sites": 0, "frontier_mismatch": 0,
+           "argmax_entries": 0, "argmax_mismatch": 0, "flag_windows": 0, "flag_mismatch": 0, "streams_with_any_mismatch": 0}
+    for s in range(n_check):
+        z = np.load(dump_prefix + "%d.npz" % s)
+        want = z["head"]
+        err = float(np.abs(heads[s].astype(np.float64) - want).max()) / max(float(np.abs(want).max()), 1e-30)
+        out["head_max_rel_err"] = max(out["head_max_rel_err"], err)
+        any_bad = False
+        for i, nm in enumerate(net.names):
+            hh, ww = net.infos[i].height, net.infos[i].width
+            wf = np.unpackbits(z["front_" + nm])[:hh * ww].reshape(hh, ww).astype(bool)
+            gf = net.frontier(i, s)
+            out["frontier_sites"] += int(wf.sum())
+            d = int((gf ^ wf).sum())
+            out["frontier_mismatch"] += d
+            any_bad |= d > 0
+            if "idx_" + nm in z:
+                st = net.state(i, s)
+                wi = z["idx_" + nm]
+                wfl = np.unpackbits(z["flags_" + nm])[:hh * ww].reshape(hh, ww).astype(bool)
+                out["argmax_entries"] += wi.size
+                d = int((st["idx"] != wi).sum())
+                out["argmax_mismatch"] += d
+                any_bad |= d > 0
+                out["flag_windows"] += wfl.size
+                d = int((st["flags"] != wfl).sum())
+                out["flag_mismatch"] += d
+                any_bad |= d > 0
+        out["streams_with_any_mismatch"] += int(any_bad)
+    out["note"] = ("the CPU baseline's oracle workers and GPU streams 0..%d consume the same events; compared after the "
+                   "pre-roll + warm-up (the state the timed region starts from).  A non-zero integer mismatch on a float net "
+                   "must be a near tie of the oracle's own values: tests/test_cuda_fullsize.py::"
+                   "test_efcn_benchmark_regime_against_live_oracle asserts that over 224 steps" % (n_check - 1))
+    return out
 
 
 def native_arm(args):
@@ -220,16 +428,28 @@ def native_arm(args):
     import torch.distributed as dist
     import async_ev_cnn_b200 as P
     from async_ev_cnn_b200.engine import EventNetCuda
+    from async_ev_cnn_b200.sharding import ShardedEventNet
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    S, B, K, Wm = args.streams, args.batch, args.steps, max(args.warmup, 3)
+    n_e2e = 2 * K + 4
+    n_steps = args.preroll + Wm + 2 * K + 2 + n_e2e
 
+    # ---- CPU baseline first (before CUDA is touched in this process); its streams become GPU streams 0..P-1
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:        # before CUDA is touched in this process
-        rate, cores, st, secs = run_cpu_processes(args, fixed_steps=0)
+    chk = None
+    tmp = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, S)
+        tmp = tempfile.mkdtemp(prefix="aec_bench_")
+        chk = check_streams(args, P, cores, args.preroll + Wm, max(CPU_MAX_STEPS, n_steps))
+        path = os.path.join(tmp, "events.npy")
+        np.save(path, chk)
+        rate, cores, st, secs = run_cpu_processes(args, 0, path, Wm, cores, dump_prefix=os.path.join(tmp, "state"))
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d cores x 1 stream each, %.0f s timed per core after %d pre-roll steps (%d..%d steps of %d events, %s stream)" % (
                    cores, args.cpu_seconds, args.preroll, min(st), max(st), args.batch, args.kind)}
@@ -239,13 +459,18 @@ def native_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    S, B, K, Wm = args.streams, args.batch, args.steps, max(args.warmup, 3)
-    n_e2e = 2 * K + 4
-    n_steps = args.preroll + Wm + 2 * K + 2 + n_e2e
 
     wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
-    net = EventNetCuda(H, W, P.EFCN_LAYERS, wts, LEAK, ALPHA, "SAME", n_streams=S, device=local, max_events_per_step=max(2048, B))
+    # the product's multi-GPU object: world*S global streams, this rank owns a contiguous block of S (sharding.py)
+    shard = ShardedEventNet(H, W, P.EFCN_LAYERS, wts, LEAK, ALPHA, "SAME", n_streams=world * S, device=local,
+                            max_events_per_step=max(2048, B))
+    net = shard.net
+    assert net.n_streams == S
     ev_np = P.synthetic_events(args.kind, S, n_steps, B, H, W, seed=100 + rank)        # [S, steps, B, 3]
+    n_check = 0
+    if chk is not None:
+        n_check = chk.shape[0]
+        ev_np[:n_check] = chk[:, :n_steps]
     ev_np = np.ascontiguousarray(ev_np.transpose(1, 0, 2, 3)).reshape(n_steps, S * B, 3)   # per step: streams packed
     off_np = (np.arange(S + 1, dtype=np.int64) * B).astype(np.int32)
     ev_dev = torch.from_numpy(ev_np).cuda()
@@ -265,6 +490,12 @@ def native_arm(args):
     for _ in range(args.preroll + Wm):
         gpu_step(t)
         t += 1
+    pc = None
+    if n_check:
+        torch.cuda.synchronize()
+        pc = parity_check(net, os.path.join(tmp, "state"), n_check, t)
+    if tmp:
+        shutil.rmtree(tmp, ignore_errors=True)
     # ---- timed region: device-resident inputs, CUDA events on the launching stream
     launches0 = net.launch_count()
     net.counters(reset=True)
@@ -309,7 +540,7 @@ def native_arm(args):
         if key == "site_eval":
             key = ("conv_eval_tc" if name in tc_names else "conv_eval_simt") if "conv" in name else "pool_eval"
         by_kernel[key] = by_kernel.get(key, 0.0) + ms
-    ab = algorithmic_bytes(net, sites_per_step, sw, S, B)
+    ab = algorithmic_bytes(net, sites_per_step, sw, S, B, H, W)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -317,23 +548,26 @@ def native_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # dominant kernel of the step: the gathered GEMM on the tensor cores (k_conv_eval_tc, one launch per conv layer)
+    # dominant kernel of the step: the gathered GEMM on the tensor cores (one launch per conv layer)
     tc_ms = by_kernel.get("conv_eval_tc", 0.0)
-    fl = conv_flops(net, sites_per_step, tc_layers)
-    bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    tf32_peak = bf16 / 2.0
+    fl = sum(layer_flops(net, i, sites_per_step[i]) for i in tc_layers)
+    tf_pk, tf_src = tf32_peak(peaks, clocks.get("sm_mhz"))
     tc_tflops = fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     n_tc = max(1, len(tc_layers))
-    roofline = {"bound": "tensor", "kernel": "k_conv_eval_tc", "achieved": tc_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": tc_tflops / tf32_peak, "traffic": None,
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s bf16 / 2")
-                + " (kind::tf32 runs at half the bf16 rate; the kernel is timed inside a long step, so the sustained figure)",
-                "precision": "3xTF32 (three tcgen05.mma per product for fp32-grade results): the ceiling for useful FLOPs is peak / 3",
-                "frac_of_3xtf32_ceiling": 3.0 * tc_tflops / tf32_peak,
+    table = layer_table(net, prof, sites_per_step, S, tf_pk, peak)
+    issued = sum(table[net.names[i]].get("issued_TFLOPs", 0.0) * table[net.names[i]]["ms"] for i in tc_layers)
+    roofline = {"bound": "tensor", "kernel": "k_conv_eval_tc", "achieved": tc_tflops, "peak": tf_pk, "unit": "TFLOP/s",
+                "frac": tc_tflops / tf_pk, "traffic": None, "peak_source": tf_src,
+                "precision": "3xTF32 (two or three tcgen05.mma.kind::tf32 per product for fp32-grade results): `achieved` counts "
+                             "USEFUL FLOPs (2 x sites x {value, rate} x K x Cout); `issued` what the tensor pipe was asked to do, "
+                             "padding rows and split products included",
+                "issued_TFLOPs": issued / tc_ms if tc_ms > 0 else 0.0,
+                "issued_frac_of_peak": (issued / tc_ms / tf_pk) if tc_ms > 0 else 0.0,
                 "algorithmic_flops_per_launch": fl / n_tc, "launches_per_step": len(tc_layers), "kernel_ms": tc_ms / n_tc,
                 "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
                 "ms_by_kernel": {k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
                 "ms_by_launch": {k: round(v, 4) for k, v in prof.items()},
+                "layers": table,
                 "sites_per_step_per_stream": {nm: round(float(sites_per_step[i]) / S, 1) for i, nm in enumerate(net.names) if i}}
     # DRAM traffic per launch from the committed ncu --set full capture of the same workload (profiles/traffic.json)
     try:
@@ -358,38 +592,45 @@ def native_arm(args):
                         sw.get("swept_pool_elems", sw["live_pool_elems"]), sw["pool_elems"]),
                     "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms_total / K * 1e-3) / 1e9,
                                    "frac": ab["total"] / (ms_total / K * 1e-3) / 1e9 / peak,
-                                   "survey_8d": {"note": "SURVEY 8(d) formula as written (dense leak pass, 12 B per conv element, + measured frontier terms): "
-                                                         "the sparse sweep moves fewer bytes than this, so this figure can exceed what DRAM really carried",
-                                                 "algorithmic_bytes": ab["total_survey_8d"],
-                                                 "achieved_gbs": ab["total_survey_8d"] / (ms_total / K * 1e-3) / 1e9,
-                                                 "frac": ab["total_survey_8d"] / (ms_total / K * 1e-3) / 1e9 / peak}}}
+                                   "note": "bytes the implemented algorithm needs (sparse leak sweep + measured frontier terms, SURVEY 8(d) "
+                                           "with the leak term restricted to the sites that are swept)"}}
     if same:
         roofline_hbm["traffic"] = tj["dram_bytes_per_launch"].get("k_leak_sweep")
 
-    # ---- end to end through the public host API: pinned host events in, head out, every step.
-    # (a) blocking call per step (aec_net_step_host), (b) the pipelined form (aec_net_step_host_async: two steps
-    # in flight, the copies of neighbouring steps overlap the kernels) - (b) is the throughput a user gets.
+    # ---- end to end through the multi-GPU product path (ShardedEventNet): pinned host events in; every rank's head is
+    # copied by its own GPU straight into its rows of ONE shared page-locked host array, so after sync() rank 0 holds
+    # the assembled [world*S, 5, 7, 110] detections ("gathered on the host", north_star) - no collective, no staging.
+    # (a) the pipelined form (two steps in flight, copies overlap the kernels) is the throughput a user gets,
+    # (b) the blocking form waits for the assembled detections of every step before the next one starts.
     ev_host = torch.from_numpy(ev_np[t:t + n_e2e]).pin_memory()
     off_host = torch.from_numpy(off_np).pin_memory()
-    head_bufs = [torch.empty((S,) + net.head_shape, dtype=torch.float32).pin_memory() for _ in range(2)]
     evh, offh = ev_host.numpy(), off_host.numpy()
-    headh = [hb.numpy() for hb in head_bufs]
-    net.step_packed(evh[0], offh, out=headh[0], cuda_stream=sh)       # warm both paths (staging buffers, copy streams)
-    net.step_packed_async(evh[1], offh, headh[1], cuda_stream=sh)
-    net.host_sync(sh)
+    shard.open_host_gather(slots=2)
+    shard.step_packed_async(evh[0], offh, cuda_stream=sh)          # warm the path (staging buffers, copy streams)
+    shard.step_packed_async(evh[1], offh, cuda_stream=sh)
+    shard.sync(sh)
     half = max(3, n_e2e // 2)
     barrier()
     w0 = time.perf_counter()
+    last_slot = 0
     for i in range(2, half):
-        net.step_packed_async(evh[i], offh, headh[i & 1], cuda_stream=sh)
-    net.host_sync(sh)
+        last_slot = shard.step_packed_async(evh[i], offh, cuda_stream=sh)
+    shard.sync(sh)                                                  # every rank's rows of every enqueued step are in host memory
     e2e_s = time.perf_counter() - w0
     e2e_steps = half - 2
+    assembled = None
+    if rank == 0:
+        a = shard.assembled(last_slot)
+        blocks = [float(np.abs(a[r * S:(r + 1) * S]).sum()) for r in range(world)]
+        assembled = {"shape": list(a.shape), "abs_sum": float(sum(blocks)), "rank_blocks_nonzero": int(sum(b > 0 for b in blocks)),
+                     "finite": bool(np.isfinite(a).all()),
+                     "where": "one POSIX shared-memory array on the host, page-locked by every rank (cudaHostRegister); each rank's "
+                              "device-to-host copy writes its own rows"}
     barrier()
     w0 = time.perf_counter()
     for i in range(half, n_e2e):
-        net.step_packed(evh[i], offh, out=headh[0], cuda_stream=sh)
-    torch.cuda.synchronize()
+        shard.step_packed_async(evh[i], offh, cuda_stream=sh)
+        shard.sync(sh)
     sync_s = time.perf_counter() - w0
     sync_steps = n_e2e - half
     if world > 1:
@@ -398,7 +639,7 @@ def native_arm(args):
         e2e_s, sync_s = float(tt[0].item()), float(tt[1].item())
     e2e_value = world * S * B * e2e_steps / e2e_s
     e2e_sync_value = world * S * B * sync_steps / sync_s
-    checksum = float(np.abs(headh[0]).sum() + np.abs(headh[1]).sum())
+    head_bytes = int(np.prod((S,) + net.head_shape)) * 4
 
     # ---- sustained rate: the same step back to back for a few seconds (the board reaches its 1 kW power cap after
     # about a second of this).  The event batches are reused with their timestamps shifted forward by the length of
@@ -427,6 +668,10 @@ def native_arm(args):
                          "after_seconds": args.sustained_seconds, "steps_run": done,
                          "note": "last 32 of the back-to-back steps (event batches reused, timestamps shifted forward at every wrap), "
                                  "rank 0's GPU, at the 1 kW power cap"}
+    state_bytes, device_bytes = net.state_bytes_per_stream(), net.device_bytes()
+    shard.close()
+    del ev_dev
+    torch.cuda.empty_cache()
 
     # ---- single-stream latency (the reference's own operating point: batch_size 1, one network object = one stream)
     latency = None
@@ -446,28 +691,53 @@ def native_arm(args):
                    "api": "aec_net_step_host, one stream, host events in / host head out per call"}
         one.close()
 
+    # ---- BASELINE configs 4 and 5 in the same run (one GPU): stream-count sweep, saturated streams, the stress net
+    legs = None
+    if rank == 0 and world == 1 and not args.no_legs:
+        KL = max(1, args.leg_steps)
+        legs = {}
+        specs = [("uniform_S%d" % S, P.EFCN_LAYERS, H, W, S, B, "uniform", args.preroll, 0.4),
+                 ("edge_S256", P.EFCN_LAYERS, H, W, 256, B, "edge", args.preroll, 0.4),
+                 ("edge_S4096", P.EFCN_LAYERS, H, W, 4096, B, "edge", args.preroll, 0.4),
+                 ("stress_256x320_deeper_B1000", STRESS_LAYERS, STRESS_H, STRESS_W, 256, 1000, "edge", max(args.preroll, 200), STRESS_RATE),
+                 ("stress_256x320_deeper_B2000", STRESS_LAYERS, STRESS_H, STRESS_W, 256, 2000, "edge", max(args.preroll, 200), STRESS_RATE)]
+        for name, layers, h, w, s_, b_, kind, pre, rate in specs:
+            try:
+                legs[name] = run_leg(torch, P, EventNetCuda, name, layers, h, w, s_, b_, kind, pre, KL, local, peaks, rate=rate)
+            except Exception as e:                       # a leg must not take the headline down with it
+                legs[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
+        legs["note"] = ("BASELINE configs 4 (256-4096 concurrent streams; uniform = every site on the frontier) and 5 (DAVIS346-sized frame "
+                        "cropped to 256x320, ~10 Mev/s per stream, deeper EFCN variant: two 3x3 convs in the first two stages), each measured "
+                        "like the headline: pre-roll, K timed steps between CUDA events on device-resident events, K profiled steps")
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, S),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(evh[0].nbytes + offh.nbytes),
-                    "d2h_bytes_per_step": int(headh[0].nbytes), "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-                    "api": "aec_net_step_host_async + aec_net_host_sync (pipelined, 2 steps in flight, pinned host buffers)",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (evh[0].nbytes + offh.nbytes)),
+                    "d2h_bytes_per_step": int(world * head_bytes), "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "api": "ShardedEventNet.step_packed_async + sync (aec_net_step_host_async + aec_net_host_sync per rank: pipelined, "
+                           "2 steps in flight, pinned host buffers; bytes are the whole job's)",
+                    "assembled_on_rank0": assembled,
                     "blocking_api": {"value": e2e_sync_value, "ms_per_step": 1e3 * sync_s / sync_steps, "steps": sync_steps,
-                                     "api": "aec_net_step_host (one blocking call per step)"},
-                    "head_abs_sum": checksum},
+                                     "api": "step_packed_async + sync after every step: the assembled detections of step t are on rank 0's "
+                                            "host before step t+1 starts"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "state_bytes_per_stream": net.state_bytes_per_stream(), "device_bytes": net.device_bytes(),
+            "state_bytes_per_stream": state_bytes, "device_bytes": device_bytes,
         }
+        if pc is not None:
+            line["parity_check"] = pc
         if sustained is not None:
             line["sustained"] = sustained
         if latency is not None:
             line["single_stream"] = latency
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if legs is not None:
+            line["legs"] = legs
         print(json.dumps(line))
-    net.close()
     if world > 1:
         dist.destroy_process_group()
 

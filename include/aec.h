@@ -160,6 +160,12 @@ int aec_net_host_sync(aec_net *net, void *cuda_stream);
 /* Device pointer / element count of the head buffer written by the last step. */
 const float *aec_net_head_device(const aec_net *net);
 size_t aec_net_head_elems_per_stream(const aec_net *net);
+/*
+ * Copies the last step's head of streams [first_stream, first_stream + n) to HOST memory
+ * (float32 [n][H_last][W_last][C_last]) after waiting for `cuda_stream`: the read-back that goes with
+ * aec_net_step_device (graph()'s return value, event_numpy.py:101-103, for a subset of the streams).
+ */
+int aec_net_read_head(aec_net *net, int first_stream, int n, float *host_out, void *cuda_stream);
 
 /*
  * Layer-at-a-time interface mirroring Layer.compute(events, delta_leak) (layer.py:38-44), used by
@@ -261,6 +267,15 @@ int aec_net_sweep_stats(aec_net *net, unsigned long long *out8);
  * total / waiting for accumulator, site info; loader total / waiting; CTAs; units).  Synchronises.
  */
 int aec_net_tc_timing(aec_net *net, int enable, int layer, unsigned long long *out16);
+
+/*
+ * Measurement helper: how conv layer `layer` is mapped onto the tensor cores, for the "issued FLOPs" column of the
+ * roofline table.  out8 = { 1 if the layer runs on the tcgen05 kernel else 0, sites per work unit,
+ * tensor FLOPs ISSUED per unit over all weight tiles (every tcgen05.mma counted as 2*M*N*K with its padding rows
+ * and all split-precision products), 8-wide K steps, MMAs per K step and weight tile, weight tiles, kernel variant
+ * id, 0 }.  Returns 0, or a negative code for a bad layer index.
+ */
+int aec_net_tc_geometry(const aec_net *net, int layer, long long *out8);
 
 /* Number of kernels this library has launched since creation of `net` (for bench `gpu_launches`). */
 unsigned long long aec_net_launch_count(const aec_net *net);

@@ -65,6 +65,34 @@ def test_efcn_event_equals_dense_torch_frame_network():
     net.close()
 
 
+@pytest.mark.parametrize("kind", ["edge", "uniform"])
+def test_efcn_benchmark_regime_against_live_oracle(kind):
+    """The regime bench.py measures (BASELINE config 2): EFCN 160x224, B = 200, sweep skipping on, compared with the
+    live oracle step by step from reset THROUGH the 160-step settling phase and 64 steps of the steady state behind it
+    (sticky pool flags saturated, the leak sweep skipping what the step re-evaluates).  Every step: surface and
+    surface events exact, the integer decisions bit-exactly the reference's rules on the CUDA path's own maps, float
+    maps within 1e-4 of the scale, and any integer difference from the oracle explained by a near tie in the
+    oracle's own values.  The counters of both phases go to the parity log (profiles/parity_r2.json)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from parity import OracleAdapter, compare_live, record_parity
+    from async_ev_cnn_b200.engine import CudaAdapter
+    from oracle.event_oracle import OracleEventNet
+    settle, steady = 160, 64
+    wts = P.xavier_weights(P.EFCN_LAYERS, seed=0)
+    evs = P.synthetic_events(kind, 1, settle + steady, 200, H, W, seed=100)[0]
+    net = EventNetCuda(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=2)
+    ora = OracleEventNet(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME")
+    ad, oa = CudaAdapter(net, stream=1), OracleAdapter(ora)
+    a = compare_live(ad, oa, list(evs[:settle]), exact=False)
+    record_parity("live/efcn160x224_%s_steps0-%d_settling" % (kind, settle - 1), a)
+    b = compare_live(ad, oa, list(evs[settle:]), exact=False, carry=a.carry)
+    record_parity("live/efcn160x224_%s_steps%d-%d_steady_state" % (kind, settle, settle + steady - 1), b)
+    st = net.sweep_stats()
+    assert st["swept_conv_elems"] < st["live_conv_elems"], "the steady state is where the sweep skips work"
+    net.close()
+
+
 STRESS_LAYERS = ("conv1=3,3,1,16 conv1b=3,3,16,16 pool1=2,2 conv2=3,3,16,32 conv2b=3,3,32,32 pool2=2,2 conv3=3,3,32,64 pool3=2,2 "
                  "conv4=3,3,64,128 pool4=2,2 conv5=3,3,128,256 pool5=2,2 conv6=1,1,256,512 conv7=1,1,512,110")
 
@@ -75,7 +103,7 @@ def test_stress_config_davis346_deeper_variant_against_live_oracle():
     reference has no such config; its layers are generic, so the oracle runs it."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from parity import OracleAdapter, compare_live
+    from parity import OracleAdapter, compare_live, record_parity
     from async_ev_cnn_b200.engine import CudaAdapter
     from oracle.event_oracle import OracleEventNet
     h, w, steps = 256, 320, 10
@@ -84,7 +112,7 @@ def test_stress_config_davis346_deeper_variant_against_live_oracle():
     net = EventNetCuda(h, w, STRESS_LAYERS, wts, 5e-5, 0.1, "SAME", n_streams=2, max_events_per_step=4096)
     ora = OracleEventNet(h, w, STRESS_LAYERS, wts, 5e-5, 0.1, "SAME")
     mm = compare_live(CudaAdapter(net, stream=1), OracleAdapter(ora), list(evs), exact=False)
-    print("\n[parity] stress 256x320 deeper EFCN: %r" % mm)
+    record_parity("live/stress256x320_deeper_edge_10steps", mm)
     assert net.head_shape == (8, 10, 110)
     net.close()
 

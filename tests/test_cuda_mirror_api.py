@@ -90,6 +90,38 @@ def test_model_class_graph_contract():
         YoloEventCuda(h, w, 2, layers + " fc1=168,10", "SAME", 4, 6, 1, 0.1, 0.001, "random:5").build_graph(None)
 
 
+def test_multi_stream_graph_returns_fresh_arrays_and_validates_reset():
+    """graph() with n_streams > 1: a caller may keep results across steps (runner.py:100 appends them), so two
+    consecutive outputs must not alias; a scalar truthy reset (np.True_, 1) is a full reset, a mask of the wrong
+    length is rejected instead of being read out of bounds."""
+    layers = "conv1=3,3,1,4 pool1=2,2 conv2=1,1,4,7"
+    h, w, S = 16, 24, 3
+    model = YoloEventCuda(h, w, 2, layers, "SAME", 8, 12, 1, 0.1, 0.001, "random:1", n_streams=S)
+    graph = model.build_graph(None)
+    evs = P.synthetic_events("uniform", S, 4, 20, h, w, seed=3, dt_int=(1, 20))
+    a = graph([evs[s, 0] for s in range(S)], True)
+    keep = a.copy()
+    b = graph([evs[s, 1] for s in range(S)], False)
+    assert not np.shares_memory(a, b) and np.array_equal(a, keep) and not np.array_equal(a, b)
+    first = graph([evs[s, 0] for s in range(S)], np.True_)             # numpy bool scalar: full reset
+    assert np.array_equal(first, keep)
+    graph([evs[s, 1] for s in range(S)], False)
+    again = graph([evs[s, 0] for s in range(S)], 1)                    # truthy int: full reset
+    assert np.array_equal(again, keep)
+    one = graph([evs[s, 1] if s != 1 else evs[1, 0] for s in range(S)], [0, 1, 0])   # stream 1 restarts, the others go on
+    assert np.array_equal(one[1], keep[1]) and np.array_equal(one[0], b[0])
+    with pytest.raises(ValueError):
+        graph([evs[s, 2] for s in range(S)], [1, 0])                   # mask shorter than n_streams
+    with pytest.raises(ValueError):
+        model.net.reset(np.uint8(1))                                   # 0-d mask
+    with pytest.raises(ValueError):
+        model.net.step_packed(np.zeros((2, 3), np.int32), np.array([0, 1, 2, 2], np.int32), out=np.empty((S, 8, 12, 6), np.float32))
+    with pytest.raises(Exception):                                     # offsets that do not end at total / decrease
+        model.net.step_packed(np.zeros((2, 3), np.int32), np.array([0, 2, 1, 2], np.int32))
+    with pytest.raises(Exception):
+        model.net.step_packed(np.zeros((2, 3), np.int32), np.array([1, 1, 2, 2], np.int32))
+
+
 def test_runner_feeds_chunks_and_resets_per_sample(capsys):
     """CudaEventRunner.run: a sample is split into batch_event_size chunks, reset_state only on the first chunk
     (runner.py:64-72,101 as intended); the result equals feeding the oracle the same chunks."""

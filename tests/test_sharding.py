@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import async_ev_cnn_b200 as P
-from async_ev_cnn_b200.sharding import gather_detections, owner_of, shard_bounds, shard_events, shard_reset_mask
+from async_ev_cnn_b200.sharding import SharedHostGather, gather_detections, owner_of, shard_bounds, shard_events, shard_reset_mask
 
 LAYERS = "conv1=3,3,1,4 pool1=2,2 conv2=1,1,4,5"
 H, W, STEPS, BATCH = 16, 24, 6, 10
@@ -100,3 +100,51 @@ def test_gloo_sharded_run_equals_single_process(world, n_streams):
     want = _heads_for(range(n_streams))
     assert got.shape == want.shape
     assert np.array_equal(got, want)          # same oracle, same streams: sharding must not change a bit
+
+
+def _shm_worker(rank, world, port, n_streams, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = SharedHostGather(n_streams, (H // 2, W // 2, 5), slots=2, pin=False)
+        lo, hi = shard_bounds(n_streams, world, rank)
+        for slot, seed in ((0, 11), (1, 40)):                # two steps in flight, one slot each
+            g.mine(slot)[...] = _heads_for(range(lo, hi), seed=seed)
+        g.complete()
+        if rank == 0:
+            q.put((np.array(g.assembled(0)), np.array(g.assembled(1))))
+        else:
+            assert g.assembled(0) is None
+        dist.barrier()
+        g.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_streams", [(2, 5), (3, 7)])
+def test_shared_host_gather_assembles_in_global_stream_order(world, n_streams):
+    """The one-box gather of bench.py / ShardedEventNet.step_packed_async: every rank writes its rows of a shared
+    host array (on the GPU box: the D2H target of its head), rank 0 reads the assembled detections after a barrier."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shm_worker, args=(r, world, port, n_streams, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    a, b = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert np.array_equal(a, _heads_for(range(n_streams), seed=11))
+    assert np.array_equal(b, _heads_for(range(n_streams), seed=40))
+
+
+def test_shared_host_gather_single_process():
+    g = SharedHostGather(3, (2, 2), slots=1, pin=False)
+    g.mine(0)[...] = 7.0
+    g.complete()
+    assert g.assembled(0).shape == (3, 2, 2) and float(g.assembled(0).sum()) == 84.0
+    g.close()
