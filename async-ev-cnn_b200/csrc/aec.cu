@@ -46,6 +46,7 @@ struct HostLayer {
     int C = 0, H = 0, W = 0, Ww = 0;
     int Cin = 0, Hin = 0, Win = 0;
     int kh = 0, kw = 0, stride = 1, pad_t = 0, pad_l = 0;
+    SiteCode code = {0, 0};     // work-list entry coding of this layer's sites (stream << sh_s | y << sh_y | x)
     float alpha = 0.f;
     int K = 0, Kpad = 0, Npad = 0, BN = 0;
     long long fstride = 0;      // conv: floats per stream; pool: idx bytes per stream
@@ -60,6 +61,7 @@ struct HostLayer {
     bool tc = false;
     int KB = 0, Mrows = 0, Mch = 0, rep = 1, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
     bool tc_fast_decode = false;   // which site-decoder variant of k_conv_eval_tc the layer runs (fixed at finalize)
+    bool tc_sm = false;            // sites-as-M form of the kernel (Cout <= 64, multiple of 4): aec_tc.cuh
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
@@ -203,6 +205,24 @@ extern "C" int aec_net_create(aec_net **out, int device, int n_streams, int heig
     return AEC_OK;
 }
 
+static int bits_for(int n)          // bits needed for values 0 .. n-1 (at least 1)
+{
+    int b = 1;
+    while ((1 << b) < n) ++b;
+    return b;
+}
+
+// Work-list entries are 32-bit: stream << sh_s | y << sh_y | x must fit.
+static int set_site_code(const aec_net *n, HostLayer &l)
+{
+    l.code.sh_y = bits_for(l.W);
+    l.code.sh_s = l.code.sh_y + bits_for(l.H);
+    if (l.code.sh_s >= 32 || ((unsigned long long)n->S << l.code.sh_s) > (1ULL << 32))
+        return fail(AEC_EINVAL, "%d streams of %dx%d sites do not fit the 32-bit work-list entries (stream << %d | y << %d | x)", n->S, l.H, l.W,
+                    l.code.sh_s, l.code.sh_y);
+    return AEC_OK;
+}
+
 static void same_pad(int size, int k, int stride, int *before)
 {
     int total = (size % stride == 0) ? (k - stride > 0 ? k - stride : 0) : (k - size % stride > 0 ? k - size % stride : 0);
@@ -233,6 +253,11 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
     l.rep = 1;                                                      // copies of the channels along M (narrow layers: parallel epilogue)
     if (l.m_tiles == 1 && l.Mch == 32) l.rep = 4;                   // measured: pays for 32 channels (one live epilogue warp otherwise); for 64
                                                                     // the larger weight stages (2 instead of 4 in flight) cost more than they give
+    // Narrow layers take the sites-as-M form (AEC_TC_SM=0 keeps the weights-as-M form for A/B runs): the weight tile is
+    // [W_hi ; W_lo] with Cpad = channels rounded up to 16 rows each (MMA N must be a multiple of 16), no row copies.
+    const char *sm_env = getenv("AEC_TC_SM");
+    l.tc_sm = l.C <= 64 && l.C % 4 == 0 && !(sm_env && atoi(sm_env) == 0);
+    if (l.tc_sm) { l.Mch = (l.C + 15) / 16 * 16; l.rep = 1; }
     l.Mrows = l.Mch * l.rep;
     l.mtu = std::min(l.m_tiles, tc::kMaxMtu);
     l.n_acc = l.mtu == 1 ? 2 : 1;
@@ -299,6 +324,7 @@ extern "C" int aec_net_add_conv(aec_net *n, int k_h, int k_w, int c_in, int c_ou
     for (int k = 0; k < l.K; ++k)          // HWIO flattened is already [k = (ky,kx,ci)][co]
         for (int c = 0; c < c_out; ++c) l.h_w[(size_t)k * l.Npad + c] = kernel_hwio[(size_t)k * c_out + c];
     for (int c = 0; c < c_out; ++c) l.h_b[c] = bias[c];
+    { int rc = set_site_code(n, l); if (rc) return rc; }
     build_tc_image(l, p.type != AEC_LAYER_INTEGRATION, kernel_hwio);
     n->L.push_back(std::move(l));
     return (int)n->L.size() - 1;
@@ -325,6 +351,7 @@ extern "C" int aec_net_add_pool(aec_net *n, int k_h, int k_w, int stride)
     l.W = (p.W - k_w) / stride + 1;
     l.Ww = (l.W + 31) / 32;
     l.fstride = pad4((long long)l.H * l.W * l.C);
+    { int rc = set_site_code(n, l); if (rc) return rc; }
     n->L.push_back(std::move(l));
     return (int)n->L.size() - 1;
 }
@@ -459,13 +486,14 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
     p.wimg = l.wimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.Mch = l.Mch; p.rep = l.rep; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
-    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
 
     p.debug = n->tc_debug;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
-    if (l.tc_fast_decode) tc::k_conv_eval_tc<true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
-    else tc::k_conv_eval_tc<false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    if (l.tc_sm) tc::k_conv_eval_tc<true, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    else if (l.tc_fast_decode) tc::k_conv_eval_tc<true, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    else tc::k_conv_eval_tc<false, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st);
 }
@@ -480,7 +508,7 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
         p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
         p.S = n->surface; p.sstride = (long long)n->L[0].H * n->L[0].W; p.Hin = n->L[0].H; p.Win = n->L[0].W;
         p.wgt = l.wgt; p.bias = l.bias; p.Npad = l.Npad; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
-        p.C = l.C; p.H = l.H; p.W = l.W; p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+        p.C = l.C; p.H = l.H; p.W = l.W; p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
         if (l.kh == 3 && l.kw == 3) k_conv_stencil<3, 3><<<n->num_sms * 8, kThreads, 0, st>>>(p);
         else k_conv_stencil<0, 0><<<n->num_sms * 8, kThreads, 0, st>>>(p);
         int rc = launch_check(n, "k_conv_stencil");
@@ -491,7 +519,7 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
     p.src = make_src(n, li - 1);
     p.wgt = l.wgt; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.Kpad = l.Kpad; p.Npad = l.Npad;
-    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
     switch (l.BN) {
     case 16: k_conv_eval<16, 2, 4, 16><<<n->conv_eval_blocks[0], kThreads, 0, st>>>(p); break;
     case 32: k_conv_eval<32, 4, 4, 16><<<n->conv_eval_blocks[1], kThreads, 0, st>>>(p); break;
@@ -510,7 +538,7 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
     p.F = c.F; p.A = c.A; p.fstride = c.fstride; p.alpha = c.alpha; p.cW = c.W;
     p.idx = l.idx; p.Fp = l.Fp; p.Ap = l.Ap; p.pstride = l.fstride; p.flags = l.flags;
-    p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride; p.code = l.code;
     if (l.C % 4 == 0 && l.kh == 2 && l.kw == 2 && l.stride == 2) k_pool_eval<4, true><<<n->num_sms * 8, kThreads, 0, st>>>(p);
     else if (l.C % 4 == 0) k_pool_eval<4, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
     else k_pool_eval<1, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
@@ -530,7 +558,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
         p.prev_front = pv.front; p.front = l.front; p.signchg = l.signchg; p.nzr = l.nzr; p.prev_nzr = pv.nzr; p.active = n->active;
         p.sites = l.sites; p.counter = n->counts + li;
         p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
-        p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+        p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
         const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4;
         k_conv_frontier<<<n->S, kThreads, smem, st>>>(p);
         if ((rc = launch_check(n, "k_conv_frontier"))) return rc;
@@ -542,7 +570,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     p.prev_front = pv.front; p.front = l.front; p.flags = l.flags; p.nzr = l.nzr; p.prev_nzr = pv.nzr; p.active = n->active;
     p.sites = l.sites; p.counter = n->counts + li;
     p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
-    p.kh = l.kh; p.kw = l.kw; p.stride = l.stride;
+    p.kh = l.kh; p.kw = l.kw; p.stride = l.stride; p.code = l.code;
     const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4;
     k_pool_frontier<<<n->S, kThreads, smem, st>>>(p);
     if ((rc = launch_check(n, "k_pool_frontier"))) return rc;
@@ -708,7 +736,7 @@ extern "C" int aec_net_finalize(aec_net *n)
             const HostLayer &l = n->L[li], &pv = n->L[li - 1];
             FrontLayer &f = tab[li];
             f.type = l.type; f.Hin = pv.H; f.Win = pv.W; f.WwIn = pv.Ww; f.H = l.H; f.W = l.W; f.Ww = l.Ww;
-            f.kh = l.kh; f.kw = l.kw; f.pad_t = l.pad_t; f.pad_l = l.pad_l; f.stride = l.stride;
+            f.kh = l.kh; f.kw = l.kw; f.pad_t = l.pad_t; f.pad_l = l.pad_l; f.stride = l.stride; f.code = l.code;
             f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.skip = l.skip; f.sites = l.sites; f.counter = n->counts + li;
             mw = std::max(mw, std::max(pv.H * pv.Ww, std::max(pv.H * l.Ww, l.H * l.Ww)));
         }
@@ -765,7 +793,8 @@ extern "C" int aec_net_finalize(aec_net *n)
             }
         if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
         if (tc_max) {
-            const void *variants[2] = {(const void *)tc::k_conv_eval_tc<false>, (const void *)tc::k_conv_eval_tc<true>};
+            const void *variants[3] = {(const void *)tc::k_conv_eval_tc<false, false>, (const void *)tc::k_conv_eval_tc<true, false>,
+                                       (const void *)tc::k_conv_eval_tc<true, true>};
             for (const void *fn : variants) {
                 cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max);
                 if (e != cudaSuccess) return fail(AEC_ECUDA, "cannot opt in to %zu bytes of dynamic shared memory for the tensor-core conv kernel: %s", tc_max, cudaGetErrorString(e));
@@ -797,7 +826,7 @@ extern "C" int aec_net_finalize(aec_net *n)
     for (size_t li = 1; li < n->L.size(); ++li) {
         HostLayer &l = n->L[li];
         const int HW = l.H * l.W;
-        k_all_sites<<<(HW + kThreads - 1) / kThreads, kThreads, 0, st>>>(l.sites, n->counts + li, HW);
+        k_all_sites<<<(HW + kThreads - 1) / kThreads, kThreads, 0, st>>>(l.sites, n->counts + li, l.H, l.W, l.code);
         if ((rc = launch_check(n, "k_all_sites"))) return rc;
         if (l.type == AEC_LAYER_CONV) {
             if ((rc = run_conv_eval(n, (int)li, st))) return rc;
@@ -1292,11 +1321,17 @@ extern "C" int aec_net_tc_geometry(const aec_net *n, int layer, long long *out8)
     const long long k8 = (l.K + 7) / 8;
     out8[0] = 1;
     out8[1] = tc::kUnitSites;
-    out8[4] = 3;                                                   // W_hi.X_lo + W_lo.X_hi + W_hi.X_hi
     out8[5] = l.m_tiles;
     out8[3] = k8;
-    out8[2] = k8 * out8[4] * l.m_tiles * 2LL * 128 * tc::kUnitCols * 8;   // every MMA is M128 x N256 x K8
-    out8[6] = l.tc_fast_decode ? 1 : 0;
+    if (l.tc_sm) {
+        out8[4] = 4;                                               // {value, rate} x {X_hi.[W_hi;W_lo] (N = 2 Cpad), X_lo.W_hi (N = Cpad)}
+        out8[2] = k8 * 2LL * (2LL * 128 * (2 * l.Mrows) * 8 + 2LL * 128 * l.Mrows * 8);
+        out8[6] = 2;
+    } else {
+        out8[4] = 3;                                               // W_hi.X_lo + W_lo.X_hi + W_hi.X_hi
+        out8[2] = k8 * out8[4] * l.m_tiles * 2LL * 128 * tc::kUnitCols * 8;   // every MMA is M128 x N256 x K8
+        out8[6] = l.tc_fast_decode ? 1 : 0;
+    }
     return AEC_OK;
 }
 

@@ -18,8 +18,10 @@
 //                                                  every input rate is 0), other sites keep theirs.  Pool: OR over the
 //                                                  window.  Maintained by the frontier kernels; the leak sweep skips
 //                                                  sites whose bit is 0 (bit 0 => rate exactly 0 => F unchanged)
-//   sites     uint32 [S*max(H_l*W_l)]              gathered work list of the layer being updated:
-//                                                  entry = stream*H_l*W_l + y*W_l + x, streams batched
+//   sites     uint32 [S*max(H_l*W_l)]              gathered work list of the layer being updated, streams batched:
+//                                                  entry = stream << sh_s | y << sh_y | x with sh_y = bits(W_l - 1),
+//                                                  sh_s = sh_y + bits(H_l - 1) (SiteCode): sorted like the row-major
+//                                                  site index, decoded with two shifts instead of two divisions
 //
 // Semantics follow the reference line by line (citations at each kernel); the work decomposition is
 // new: frontiers are bitmaps (dedup and ordering for free), the leak of ALL conv layers is one
@@ -53,6 +55,21 @@ struct Src {
     long long fstride;
     float alpha;
 };
+
+// Work-list entry coding of one layer (see `sites` above).
+struct SiteCode {
+    int sh_y, sh_s;
+};
+__device__ __forceinline__ uint32_t site_encode(const SiteCode c, int s, int y, int x)
+{
+    return ((uint32_t)s << c.sh_s) | ((uint32_t)y << c.sh_y) | (uint32_t)x;
+}
+__device__ __forceinline__ void site_decode(const SiteCode c, uint32_t e, int &s, int &y, int &x)
+{
+    s = (int)(e >> c.sh_s);
+    y = (int)((e >> c.sh_y) & ((1u << (c.sh_s - c.sh_y)) - 1u));
+    x = (int)(e & ((1u << c.sh_y) - 1u));
+}
 
 __device__ __forceinline__ float slope_of(float f, float alpha) { return f > 0.f ? 1.f : alpha; }
 
@@ -151,8 +168,8 @@ __device__ __forceinline__ uint32_t compress_even_bits(uint32_t x)
 }
 
 // Emits the set bits of a [H][Ww] bitmap held in shared memory as list entries
-// base_id + y*W + x, row-major, into sites[] at a range reserved with one atomicAdd on *counter.
-__device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int W, int Ww, uint32_t base_id,
+// base_id | y << sh_y | x (base_id = stream << sh_s), row-major, into sites[] at a range reserved with one atomicAdd on *counter.
+__device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int Ww, uint32_t base_id, int sh_y,
                                            uint32_t *sites, int *counter, int *scratch)
 {
     const int nwords = H * Ww;
@@ -173,7 +190,7 @@ __device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int W, int
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            sites[off++] = base_id + (uint32_t)(y * W + xb + b);
+            sites[off++] = base_id | ((uint32_t)y << sh_y) | (uint32_t)(xb + b);
         }
     }
 }
@@ -518,6 +535,7 @@ struct ConvFrontParams {
     int Hin, Win, WwIn;
     int H, W, Ww;
     int kh, kw, pad_t, pad_l;
+    SiteCode code;
 };
 
 __global__ void __launch_bounds__(kThreads) k_conv_frontier(ConvFrontParams p)
@@ -580,7 +598,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_frontier(ConvFrontParams p)
         const uint32_t n = N[i];
         if (n) nz[i] = (nz[i] & ~n) | (n & vdilate(i));
     }
-    emit_sites(N, p.H, p.W, p.Ww, (uint32_t)s * (uint32_t)(p.H * p.W), p.sites, p.counter, scratch);
+    emit_sites(N, p.H, p.Ww, (uint32_t)s << p.code.sh_s, p.code.sh_y, p.sites, p.counter, scratch);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -601,6 +619,7 @@ struct PoolFrontParams {
     int Hin, Win, WwIn;
     int H, W, Ww;
     int kh, kw, stride;
+    SiteCode code;
 };
 
 __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
@@ -666,7 +685,7 @@ __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
         const uint32_t wset = Wb[i];
         if (wset) nz[i] = (nz[i] & ~wset) | (wset & window_or(i));
     }
-    emit_sites(Wb, p.H, p.W, p.Ww, (uint32_t)s * (uint32_t)(p.H * p.W), p.sites, p.counter, scratch);
+    emit_sites(Wb, p.H, p.Ww, (uint32_t)s << p.code.sh_s, p.code.sh_y, p.sites, p.counter, scratch);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -682,6 +701,7 @@ struct FrontLayer {
     int type;                     // 1 conv, 2 pool (AEC_LAYER_*)
     int Hin, Win, WwIn, H, W, Ww;
     int kh, kw, pad_t, pad_l, stride;
+    SiteCode code;
     uint32_t *front, *signchg, *flags, *nzr;
     uint32_t *skip;               // [S][H*Ww] written by k_frontier_skip: a subset of this step's work set, known before the leak sweep
     uint32_t *sites;
@@ -806,7 +826,7 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
             for (int i = tid; i < nout; i += kThreads) bufA[i] = N[i];
             __syncthreads();
         }
-        emit_sites(N, L.H, L.W, L.Ww, (uint32_t)s * (uint32_t)(L.H * L.W), L.sites, L.counter, scratch);
+        emit_sites(N, L.H, L.Ww, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.sites, L.counter, scratch);
         __syncthreads();
         for (int i = tid; i < nout; i += kThreads) bufB[i] = Z[i];
         __syncthreads();
@@ -914,6 +934,7 @@ struct PoolEvalParams {
     uint32_t *flags;              // [S][H*Ww]
     int C, H, W, Ww;
     int kh, kw, stride;
+    SiteCode code;
 };
 
 struct PoolBest {
@@ -940,13 +961,12 @@ __global__ void __launch_bounds__(kThreads) k_pool_eval(PoolEvalParams p)
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.accum, (unsigned long long)n);
     const int CG = p.C / VEC;
     const long long total = (long long)n * CG;
-    const int HW = p.H * p.W;
     for (long long wi = (long long)blockIdx.x * kThreads + threadIdx.x; wi < total; wi += (long long)gridDim.x * kThreads) {
         const uint32_t e = p.sites[wi / CG];
         const int c = (int)(wi % CG) * VEC;
-        const int s = (int)(e / (uint32_t)HW);
-        const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
-        const int oy = site / p.W, ox = site - oy * p.W;
+        int s, oy, ox;
+        site_decode(p.code, e, s, oy, ox);
+        const int site = oy * p.W + ox;
         const float *Fb = p.F + (long long)s * p.fstride;
         const float *Ab = p.A + (long long)s * p.fstride;
         PoolBest best[VEC];
@@ -1033,6 +1053,7 @@ struct ConvEvalParams {
     int C, H, W;           // output
     int K, Kpad, Npad;
     int kh, kw, pad_t, pad_l;
+    SiteCode code;
 };
 
 template <int BN, int TN, int TM, int BK>
@@ -1055,7 +1076,6 @@ __global__ void __launch_bounds__(kThreads) k_conv_eval(ConvEvalParams p)
     const int n_tiles = p.Npad / BN;
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
-    const int HW = p.H * p.W;
     const int Cin = p.src.C;
     const bool vec = (Cin % 4 == 0) && (p.src.kind != 0);
 
@@ -1066,12 +1086,11 @@ __global__ void __launch_bounds__(kThreads) k_conv_eval(ConvEvalParams p)
         for (int i = tid; i < TS; i += kThreads) {
             const int gi = mt * TS + i;
             if (gi < n_sites) {
-                const uint32_t e = p.sites[gi];
-                const int s = (int)(e / (uint32_t)HW);
-                const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
+                int s, y, x;
+                site_decode(p.code, p.sites[gi], s, y, x);
                 s_str[i] = s;
-                s_y[i] = site / p.W;
-                s_x[i] = site - (site / p.W) * p.W;
+                s_y[i] = y;
+                s_x[i] = x;
             } else {
                 s_str[i] = -1;
             }
@@ -1202,6 +1221,7 @@ struct StencilParams {
     long long fstride;
     int C, H, W;           // output (C % 4 == 0)
     int kh, kw, pad_t, pad_l;
+    SiteCode code;
 };
 constexpr int kStencilMaxK = 64, kStencilMaxC = 64;
 
@@ -1221,13 +1241,12 @@ __global__ void __launch_bounds__(kThreads) k_conv_stencil(StencilParams p)
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.accum, (unsigned long long)n);
     const int CG = p.C >> 2;
     const long long total = (long long)n * CG;
-    const int HW = p.H * p.W;
     for (long long wi = (long long)blockIdx.x * kThreads + threadIdx.x; wi < total; wi += (long long)gridDim.x * kThreads) {
         const uint32_t e = p.sites[wi / CG];
         const int c = (int)(wi % CG) * 4;
-        const int s = (int)(e / (uint32_t)HW);
-        const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
-        const int y = site / p.W, x = site - y * p.W;
+        int s, y, x;
+        site_decode(p.code, e, s, y, x);
+        const int site = y * p.W + x;
         const double *Sb = p.S + (long long)s * p.sstride;
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f), a = f;
         auto tap = [&](int ky, int kx) {
@@ -1374,11 +1393,11 @@ __global__ void __launch_bounds__(kThreads) k_reset_scalars(int *prev_ts, double
 }
 
 // every site of stream 0 -> work list (used once, to evaluate the initial state)
-__global__ void __launch_bounds__(kThreads) k_all_sites(uint32_t *sites, int *counter, int HW)
+__global__ void __launch_bounds__(kThreads) k_all_sites(uint32_t *sites, int *counter, int H, int W, SiteCode code)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i < HW) sites[i] = (uint32_t)i;
-    if (i == 0) *counter = HW;
+    if (i < H * W) sites[i] = site_encode(code, 0, i / W, i % W);
+    if (i == 0) *counter = H * W;
 }
 
 }  // namespace aec

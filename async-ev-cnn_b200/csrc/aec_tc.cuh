@@ -24,6 +24,20 @@
 // with gathers, stores and MMAs knocked out conv2 still takes 72 % of its time (decoder ~8.5 k cycles per unit,
 // epilogue ~7.4 k, against a 10.9 k-cycle unit).
 //
+// Narrow layers (Cout <= 64, round 2): `kSM` = SITES are the M operand.  With the weights as M a 32- or 64-channel
+// layer fills a quarter or half of the 128 rows the tensor core computes anyway, and the profile of round 1
+// (profiles/r2_summary.md) shows the kernel bounded by shared-memory bandwidth, a large part of it the tensor core's
+// own operand reads (12 KB per MMA).  Sites-as-M turns that around:
+//     D_v[site, n] = sum_k Xv[site, k] * Wcat[n, k]      M = 128 sites (value rows; D_r likewise for the rate rows)
+//                                                        N = 2*Cpad: Wcat = [W_hi ; W_lo] stacked along N
+//   per 8-wide K step and 128 sites:  Xv_hi x Wcat (N = 2*Cpad)  +  Xv_lo x W_hi (N = Cpad, same columns as the hi.hi part)
+//                                     and the same two for the rate rows: 4 MMAs of 64 cycles (N <= 128) = 2 cycles per
+//   site instead of 3, 22-28 KB of operand reads instead of 36, and the three products of the 3xTF32 scheme
+//   (hi.hi, hi.lo, lo.hi) are still all there.  The accumulator comes out site-per-lane: an epilogue thread owns one
+//   site, adds the two column halves (W_hi part + W_lo part) and writes the site's channels as contiguous 16-byte
+//   stores.  The gather producers, the stage format and all pipelines are shared with the weights-as-M form; only
+//   where a value / rate row lands in the stage differs (tile_v = rows of 128 sites, tile_r behind it).
+//
 // Precision: north_star asks for float32 maps within 1e-4 relative, and the oracle's pool ties must
 // stay exact, so a bare TF32 product (10-bit mantissa) is not enough.  Every operand is split into
 // hi = tf32(x) and lo = x - hi (exact in fp32) and three MMAs are issued per K step:
@@ -103,21 +117,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 24)) __trap();
-}
-// Warp-level forms.  An mbarrier arrive is a shared-memory atomic per executing LANE and a try_wait a shared-memory
-// read per lane; with every thread of a role arriving and polling, those came to 42 % of the kernel's LSU
-// shared-memory wavefronts (profiles/r2a: 28 M arrive + 38 M poll wavefronts against 98 M of real operand traffic
-// per conv2 launch), on a kernel bounded by shared-memory bandwidth.  So one lane per warp polls / arrives for the
-// warp: __syncwarp orders the other lanes' accesses with it (barrier counts are per warp accordingly).
-__device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity)
-{
-    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-    __syncwarp();
-}
-__device__ __forceinline__ void warp_arrive(uint32_t bar)
-{
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -209,6 +208,7 @@ struct TcParams {
                                 // chunks with chunk % rep == g; the extra rows cost the tensor core nothing, M is 128 anyway)
     int mtu;                    // weight tiles per unit (1 or 2): the unit's sites are gathered once for all of them
     int kh, kw, pad_t, pad_l;
+    SiteCode code;              // work-list entry coding of the output layer
     int w_stages;               // weight pipeline depth
     int n_acc;                  // accumulator buffers in TMEM (2 when mtu == 1, else 1)
     unsigned long long *timing; // null, or 16 cycle counters accumulated over CTAs (aec_net_tc_timing): see TcTimingSlot
@@ -226,17 +226,6 @@ __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool o
         acc += clock64() - t0;
     } else {
         mbar_wait(bar, parity);
-    }
-}
-// the same for a whole (converged) warp: lane 0 polls
-__device__ __forceinline__ void timed_warp_wait(uint32_t bar, uint32_t parity, bool on, long long &acc)
-{
-    if (on) {
-        const long long t0 = clock64();
-        warp_wait(bar, parity);
-        acc += clock64() - t0;
-    } else {
-        warp_wait(bar, parity);
     }
 }
 
@@ -309,6 +298,7 @@ __device__ __forceinline__ void split2(float x0, float x1, float &h0, float &h1,
     l1 = l.y;
 }
 
+template <uint32_t kRateOff>
 __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uint32_t x_lo, int t, const float4 (&f)[kPairs],
                                            const float4 (&a)[kPairs])
 {
@@ -329,7 +319,7 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
         sts128(x_lo + ov, l);
         split2(w01.x, w01.y, h.x, h.y, l.x, l.y);
         split2(w23.x, w23.y, h.z, h.w, l.z, l.w);
-        const uint32_t ow = ov + (uint32_t)(kItemSites / 8) * 1024u;      // rate row = value row + 64 (same swizzle phase)
+        const uint32_t ow = ov + kRateOff;      // rate row: weights-as-M value row + 64, sites-as-M the same row of tile_r (same swizzle phase)
         sts128(x_hi + ow, h);
         sts128(x_lo + ow, l);
     }
@@ -339,7 +329,7 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
 // The weight stages come first: the A descriptor always spans 128 rows, so with Mrows < 128 it reads
 // past the tile into whatever follows (the next stage / the site stages); those rows only feed
 // accumulator lanes >= Mrows, which the epilogue never reads.
-template <bool kFastDecode>
+template <bool kFastDecode, bool kSM>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
     extern __shared__ unsigned char tc_smem_raw[];
@@ -364,7 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
 
     if (tid == 0) {
         for (int i = 0; i < kSiteStages; ++i) {
-            mbar_init(smem_u32(&bar_x_full[i]), 2 * kGroupThreads / 32); // both halves of the stage (two producer groups), one arrival per warp
+            mbar_init(smem_u32(&bar_x_full[i]), 2 * kGroupThreads);      // both halves of the stage (two producer groups)
             mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
         for (int i = 0; i < p.w_stages; ++i) {
@@ -373,11 +363,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bar_acc_full[i]), 1);
-            mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps);           // one arrival per epilogue warp
+            mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps * 32);
         }
         for (int i = 0; i < kSiteRing; ++i) {
             mbar_init(smem_u32(&bar_si_full[i]), 1);
-            mbar_init(smem_u32(&bar_si_free[i]), kEpiWarps);
+            mbar_init(smem_u32(&bar_si_free[i]), kEpiWarps * 32);
         }
         fence_barrier_init();
     }
@@ -390,7 +380,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
-    const int HW = p.H * p.W;
     const bool timing = p.timing != nullptr;
     const int n_units_cta = (total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -408,9 +397,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const int mg = unit % n_mgroups;
             const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
             const int buf = ul % kSiteRing, ab = ul % p.n_acc;
-            timed_warp_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul / kSiteRing) & 1u, timing, tw_si);
-            timed_warp_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u, timing, tw_acc);
+            timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul / kSiteRing) & 1u, timing, tw_si);
+            timed_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u, timing, tw_acc);
             tc_fence_after();
+            if constexpr (kSM) {
+                // sites-as-M: TMEM lane == site of the unit; columns [0, 2*Cpad) of the buffer are D_v (hi.hi + lo.hi products in
+                // [0, Cpad), hi.lo products in [Cpad, 2*Cpad)), the next 2*Cpad columns D_r.  One thread = one site: it adds the
+                // two halves, adds the bias to the value row and writes 4 channels per 16-byte store.
+                const int cpad = p.Mrows;
+                const long long dst = s_dst[buf][warp * 32 + lane];
+                const bool site_ok = dst >= 0 && !(p.debug & 8);
+                const uint32_t tbase = lane_addr + (uint32_t)(ab * 4 * cpad);
+                const int nch = (p.C + 15) >> 4;                       // 16-channel chunks holding real channels
+                const int total = 2 * nch;                             // value chunks, then rate chunks
+                uint32_t ra[16], rb[16], rc[16], rd[16];
+                auto issue = [&](int ci, uint32_t(&hi)[16], uint32_t(&lo)[16]) {
+                    const int map = ci >= nch ? 1 : 0, c0 = (ci - map * nch) << 4;
+                    const uint32_t ta = tbase + (uint32_t)(map * 2 * cpad + c0);
+                    tmem_ld16(ta, hi);
+                    tmem_ld16(ta + (uint32_t)cpad, lo);
+                };
+                auto emit = [&](int ci, const uint32_t(&hi)[16], const uint32_t(&lo)[16]) {
+                    const int map = ci >= nch ? 1 : 0, c0 = (ci - map * nch) << 4;
+                    if (!site_ok) return;
+                    char *const out = (char *)(map ? p.A : p.F) + dst + (long long)c0 * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (c0 + 4 * q >= p.C) break;                   // C % 4 == 0: whole float4 groups only
+                        float4 o;
+                        o.x = __fadd_rn(__uint_as_float(hi[4 * q + 0]), __uint_as_float(lo[4 * q + 0]));
+                        o.y = __fadd_rn(__uint_as_float(hi[4 * q + 1]), __uint_as_float(lo[4 * q + 1]));
+                        o.z = __fadd_rn(__uint_as_float(hi[4 * q + 2]), __uint_as_float(lo[4 * q + 2]));
+                        o.w = __fadd_rn(__uint_as_float(hi[4 * q + 3]), __uint_as_float(lo[4 * q + 3]));
+                        if (!map) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + 4 * q));
+                            o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+                        }
+                        *reinterpret_cast<float4 *>(out + 16 * q) = o;
+                    }
+                };
+                issue(0, ra, rb);
+#pragma unroll 1
+                for (int ci = 0; ci < total; ci += 2) {
+                    tmem_ld_wait();
+                    if (ci + 1 < total) issue(ci + 1, rc, rd);
+                    emit(ci, ra, rb);
+                    if (ci + 1 >= total) break;
+                    tmem_ld_wait();
+                    if (ci + 2 < total) issue(ci + 2, ra, rb);
+                    emit(ci + 1, rc, rd);
+                }
+            } else
             if (warp_live) {
                 for (int mt = 0; mt < mt_count; ++mt) {
                     const int g = p.rep > 1 ? (warp * 32) / p.Mch : 0;    // which copy of the channels this warp holds (Mch % 32 == 0 when rep > 1)
@@ -451,8 +488,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 }
             }
             tc_fence_before();
-            warp_arrive(smem_u32(&bar_acc_empty[ab]));
-            warp_arrive(smem_u32(&bar_si_free[buf]));
+            mbar_arrive(smem_u32(&bar_acc_empty[ab]));
+            mbar_arrive(smem_u32(&bar_si_free[buf]));
         }
         if (timing && tid == 0) {
             atomicAdd(p.timing + kTEpiTotal, (unsigned long long)(clock64() - t_begin));
@@ -470,6 +507,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         // that the tensor pipe idles (the wait queues behind the in-flight MMAs), so all operand waits
         // live in the gatekeeper warp, which releases each pass through a named barrier (ids 1..4).
         const uint32_t idesc = make_idesc_tf32(kUnitCols);
+        const uint32_t idesc_cat = make_idesc_tf32(kSM ? 2 * p.Mrows : kUnitCols), idesc_hi = make_idesc_tf32(kSM ? p.Mrows : kUnitCols);
         const uint32_t x_base = smem_u32(smem_x), w_base = smem_u32(smem_w);
         uint32_t qx = 0, qw = 0;
         long long tw_gate = 0;
@@ -492,7 +530,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     if (timing) tw_gate += clock64() - t0;
                     tc_fence_after();
                     if (elect_one()) {
-                        if (!(p.debug & 4)) {
+                        if constexpr (kSM) {
+                            // sites-as-M: A = one 128-row site tile (tile_v, then tile_r 16 KB behind it), B = [W_hi ; W_lo] (2*Cpad rows
+                            // of the weight stage; its first Cpad rows alone are W_hi).  X_lo x W_hi accumulates into the same columns
+                            // as X_hi x W_hi: the epilogue only has to add the W_lo half.
+                            if (!(p.debug & 4)) {
+                                const uint32_t dv = tmem_base + (uint32_t)(ab * 4 * p.Mrows), dr = dv + (uint32_t)(2 * p.Mrows);
+#pragma unroll
+                                for (int ks = 0; ks < kBlockK / 8; ++ks) {
+                                    const uint32_t ko = (uint32_t)ks * 32u;
+                                    const uint64_t dw = make_desc_sw128(w_hi + ko);
+                                    const uint64_t dvh = make_desc_sw128(x_hi + ko), dvl = make_desc_sw128(x_lo + ko);
+                                    const uint64_t drh = make_desc_sw128(x_hi + (uint32_t)kItemTileBytes + ko), drl = make_desc_sw128(x_lo + (uint32_t)kItemTileBytes + ko);
+                                    if (ks >= ks_n) break;
+                                    const uint32_t acc = (kb | ks) != 0 ? 1u : 0u;
+                                    mma_tf32(dv, dvh, dw, idesc_cat, acc);
+                                    mma_tf32(dr, drh, dw, idesc_cat, acc);
+                                    mma_tf32(dv, dvl, dw, idesc_hi, 1u);
+                                    mma_tf32(dr, drl, dw, idesc_hi, 1u);
+                                }
+                            }
+                        } else if (!(p.debug & 4)) {
 #pragma unroll
                             for (int ks = 0; ks < kBlockK / 8; ++ks) {
                                 const uint32_t ko = (uint32_t)ks * 32u;       // 8 tf32 = 32 bytes along K inside the swizzled row
@@ -530,7 +588,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
             const int ab = ul % p.n_acc;
             const uint32_t ua = (uint32_t)(ul / p.n_acc);
-            if (ua > 0) timed_warp_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
+            if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
                 const uint32_t sx = qx % (uint32_t)kSiteStages;
                 const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
@@ -538,8 +596,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
                     // every wait costs ~170 cycles even when the barrier is already complete: the weights (normally early)
                     // first, the site stage (normally the last thing to arrive) last, one barrier for both of its halves
-                    timed_warp_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
-                    if (mt == 0) timed_warp_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
+                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                    if (mt == 0) timed_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
                     asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qw & 3u)) : "memory");
                 }
             }
@@ -581,7 +639,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         // ===================== site decoder =====================
         // kFastDecode (layers with long units or several weight tiles): measured 3-4 % faster there, but 2-8 % slower for the short
         // units of the first two tensor-core layers, which keep the simple loop (profiles/r1e_summary.md).
-        const double inv_hw = 1.0 / (double)HW, inv_w = 1.0 / (double)p.W;
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
             const int blk = unit / n_mgroups;
@@ -598,7 +655,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     const long long gi = (long long)blk * kUnitSites + lane + 32 * k;
                     ent[k] = gi < n_sites ? __ldg(p.sites + gi) : 0xffffffffu;
                 }
-                if (us > 0) warp_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
+                if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
     #pragma unroll
                 for (int k = 0; k < kUnitSites / 32; ++k) {
                     const int i = lane + 32 * k;
@@ -606,13 +663,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
                     long long dst = -1;
                     if (ent[k] != 0xffffffffu) {
-                        const uint32_t e = ent[k];
-                        int s = (int)__double2uint_rz(__uint2double_rn(e) * inv_hw);       // e / HW, off by at most one
-                        int site = (int)(e - (uint32_t)s * (uint32_t)HW);
-                        if (site < 0) { --s; site += HW; } else if (site >= HW) { ++s; site -= HW; }
-                        int y = (int)__double2uint_rz(__uint2double_rn((uint32_t)site) * inv_w);
-                        int x = site - y * p.W;
-                        if (x < 0) { --y; x += p.W; } else if (x >= p.W) { ++y; x -= p.W; }
+                        int s, y, x;
+                        site_decode(p.code, ent[k], s, y, x);
+                        const int site = y * p.W + x;
                         q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
                         uint32_t colbits = 0u;
                         for (int kx = 0; kx < p.kw; ++kx)
@@ -625,17 +678,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     s_dst[buf][i] = dst;
                 }
             } else {
-                if (us > 0) warp_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
+                if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
                 for (int i = lane; i < kUnitSites; i += 32) {
                     const long long gi = (long long)blk * kUnitSites + i;
                     SiteSrc q;
                     q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
                     long long dst = -1;
                     if (gi < n_sites) {
-                        const uint32_t e = p.sites[gi];
-                        const int s = (int)(e / (uint32_t)HW);
-                        const int site = (int)(e - (uint32_t)s * (uint32_t)HW);
-                        const int y = site / p.W, x = site - y * p.W;
+                        int s, y, x;
+                        site_decode(p.code, p.sites[gi], s, y, x);
+                        const int site = y * p.W + x;
                         q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
                         for (int ky = 0, tap = 0; ky < p.kh; ++ky)
                             for (int kx = 0; kx < p.kw; ++kx, ++tap)
@@ -673,7 +725,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         auto load = [&](const Pos &c, float4 (&f)[kPairs], float4 (&a)[kPairs]) {
             const int buf = c.ul % kSiteRing;
             if (c.ul > ready_ul) {
-                timed_warp_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(c.ul / kSiteRing) & 1u, timing, tw_si);
+                timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(c.ul / kSiteRing) & 1u, timing, tw_si);
                 ready_ul = c.ul;
             }
             const KEntry e = c.kb < kKtabBlocks ? s_ktab[c.kb * 8 + (t & 7)] : make_kentry(p, c.kb, t & 7);
@@ -683,11 +735,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         auto store = [&](const Pos &c, const float4 (&f)[kPairs], const float4 (&a)[kPairs]) {
             const uint32_t qx = c.q >> 1;
             const uint32_t sx = qx % (uint32_t)kSiteStages, use = qx / (uint32_t)kSiteStages;
-            if (use > 0) timed_warp_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
-            const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes + (uint32_t)c.h * (uint32_t)kItemTileBytes;
-            item_store(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
+            if (use > 0) timed_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
+            // weights-as-M: an item's 128 rows (64 value rows, then its 64 rate rows) are one half of the 256-row tile;
+            // sites-as-M: its value rows are rows 64h.. of tile_v and its rate rows the same rows of tile_r (16 KB behind)
+            constexpr uint32_t kHalfStride = kSM ? (uint32_t)(kItemSites / 8) * 1024u : (uint32_t)kItemTileBytes;
+            constexpr uint32_t kRateOff = kSM ? (uint32_t)kItemTileBytes : (uint32_t)(kItemSites / 8) * 1024u;
+            const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes + (uint32_t)c.h * kHalfStride;
+            item_store<kRateOff>(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
             fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
-            warp_arrive(smem_u32(&bar_x_full[sx]));
+            mbar_arrive(smem_u32(&bar_x_full[sx]));
         };
         Pos cur;
         cur.q = (uint32_t)g; cur.ul = 0; cur.kb = g >> 1; cur.h = g & 1;

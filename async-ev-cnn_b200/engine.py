@@ -329,7 +329,8 @@ class EventNetCuda:
             return None
         return {"unit_sites": int(buf[1]), "mma_flops_per_unit": float(buf[2]), "m_groups": 1, "k8_steps": int(buf[3]),
                 "mma_per_kstep": int(buf[4]), "weight_tiles": int(buf[5]),
-                "kernel": "k_conv_eval_tc<%d>" % int(buf[6])}
+                "kernel": ("k_conv_eval_tc<simple decode, weights-as-M>", "k_conv_eval_tc<batched decode, weights-as-M>",
+                           "k_conv_eval_tc<sites-as-M>")[int(buf[6])]}
 
     TC_TIMING_SLOTS = ("mma_total", "mma_wait_acc", "mma_wait_sites", "mma_wait_weights", "prod_total", "prod_wait_siteinfo",
                        "prod_wait_stage", "epi_total", "epi_wait_acc", "epi_wait_siteinfo", "load_total", "load_wait", "ctas", "units",
