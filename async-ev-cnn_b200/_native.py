@@ -20,7 +20,7 @@ SYMBOLS = [
     "aec_net_step_host", "aec_net_head_device", "aec_net_head_elems_per_stream", "aec_net_read_head", "aec_net_begin_step",
     "aec_net_layer_compute", "aec_net_compute_head", "aec_net_read_size", "aec_net_read", "aec_net_read_step_info",
     "aec_net_read_counters", "aec_net_launch_count", "aec_net_read_view", "aec_net_profile", "aec_net_read_profile",
-    "aec_net_count_nonzero_rate_groups", "aec_net_tc_timing", "aec_net_tc_geometry", "aec_net_sweep_stats", "aec_net_step_host_async", "aec_net_host_sync", "aec_net_decode_head", "aec_decode_ndata",
+    "aec_net_count_nonzero_rate_groups", "aec_net_tc_timing", "aec_net_tc_geometry", "aec_net_sweep_stats", "aec_net_step_host_async", "aec_net_host_sync", "aec_net_decode_head", "aec_decode_ndata", "aec_split_batches", "aec_net_run_ndata",
 ]
 
 
@@ -86,6 +86,10 @@ def lib():
     L.aec_net_decode_head.argtypes = [vp, i, i, i, i, i, i, ctypes.c_float, vp, vp, vp, vp, vp]
     L.aec_decode_ndata.restype = i
     L.aec_decode_ndata.argtypes = [i, vp, vp, i, i, i, i, i, vp, vp, vp]
+    L.aec_split_batches.restype = i
+    L.aec_split_batches.argtypes = [i, vp, vp, i, i, i, vp, vp]
+    L.aec_net_run_ndata.restype = i
+    L.aec_net_run_ndata.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp]
     L.aec_net_head_device.restype = vp
     L.aec_net_head_device.argtypes = [vp]
     L.aec_net_head_elems_per_stream.restype = sz

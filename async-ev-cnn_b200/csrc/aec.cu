@@ -89,6 +89,7 @@ struct aec_net {
     float *head = nullptr;
     size_t head_per_stream = 0;
     int32_t *ev_dev = nullptr, *off_dev = nullptr;
+    const int32_t *ev_ends = nullptr;   // batched recordings (aec_net_run_ndata): stream s owns events off[s] .. ev_ends[s]; null otherwise
     size_t ev_cap = 0;
     // pipelined host stepping (aec_net_step_host_async): two slots of event staging / head buffers, copy streams
     struct HostSlot {
@@ -419,7 +420,7 @@ static IntegrateParams integrate_params(aec_net *n, const int32_t *ev, const int
     const HostLayer &l = n->L[0];
     IntegrateParams p;
     p.surface = n->surface; p.prev_ts = n->prev_ts; p.delta = n->delta; p.active = n->active;
-    p.front = l.front; p.alive = l.nzr; p.events = ev; p.offsets = off; p.layer_counts = n->counts; p.err_flag = n->err_flag;
+    p.front = l.front; p.alive = l.nzr; p.events = ev; p.offsets = off; p.ends = n->ev_ends; p.layer_counts = n->counts; p.err_flag = n->err_flag;
     p.n_layers = (int)n->L.size();
     p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.leak = n->leak; p.max_events = n->max_events; p.hash_slots = n->hash_slots;
     return p;
@@ -971,8 +972,8 @@ extern "C" int aec_net_step_device(aec_net *n, const int32_t *ev, const int32_t 
         }
         if (g.exec) {
             float *out = n->head_cur ? n->head_cur : n->head;
-            if (g.ip.events != ev || g.ip.offsets != off) {
-                g.ip.events = ev; g.ip.offsets = off;
+            if (g.ip.events != ev || g.ip.offsets != off || g.ip.ends != n->ev_ends) {
+                g.ip.events = ev; g.ip.offsets = off; g.ip.ends = n->ev_ends;
                 cudaKernelNodeParams kp = g.integ_kp;
                 void *args[1] = {&g.ip};
                 kp.kernelParams = args;
@@ -1403,6 +1404,140 @@ extern "C" int aec_net_decode_head(aec_net *n, int num_classes, int num_bbox, in
     if (valid_out) CU(cudaMemcpyAsync(valid_out, n->dec_valid, nb, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return AEC_OK;
+}
+
+// f1 on the device, stand-alone form (host in / host out) for parity tests against the runner's split.
+extern "C" int aec_split_batches(int device, const int32_t *events_yxt, const long long *rec_offsets, int n_recordings,
+                                 int batch_event_size, int batch_event_usec, int32_t *chunk_offsets_out, int32_t *n_chunks_out)
+{
+    if (!rec_offsets || n_recordings < 0 || !chunk_offsets_out || !n_chunks_out) return fail(AEC_EINVAL, "split_batches: bad arguments");
+    if (batch_event_usec <= 0 && batch_event_size < 1) return fail(AEC_EINVAL, "split_batches: batch_event_size must be >= 1");
+    if (n_recordings == 0) return AEC_OK;
+    if (rec_offsets[0] != 0) return fail(AEC_EINVAL, "split_batches: rec_offsets[0] must be 0");
+    for (int r = 0; r < n_recordings; ++r)
+        if (rec_offsets[r + 1] < rec_offsets[r]) return fail(AEC_EINVAL, "split_batches: rec_offsets decrease at %d", r);
+    const long long total = rec_offsets[n_recordings];
+    if (total > 0 && !events_yxt) return fail(AEC_EINVAL, "split_batches: NULL events");
+    if (total + 2LL * n_recordings >= (1LL << 31)) return fail(AEC_EINVAL, "split_batches: too many events");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(AEC_EINVAL, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    int32_t *d_ev = nullptr, *d_cnt = nullptr, *d_co = nullptr, *d_nc = nullptr;
+    long long *d_start = nullptr;
+    auto cleanup = [&]() { cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_co); cudaFree(d_nc); cudaFree(d_start); };
+#define CUF(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { cleanup(); return fail(AEC_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    std::vector<int32_t> cnt(n_recordings);
+    for (int r = 0; r < n_recordings; ++r) cnt[r] = (int32_t)(rec_offsets[r + 1] - rec_offsets[r]);
+    const size_t n_co = (size_t)total + 2 * (size_t)n_recordings;
+    CUF(cudaMalloc(&d_ev, std::max<long long>(total, 1) * 3 * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_cnt, (size_t)n_recordings * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_nc, (size_t)n_recordings * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_co, n_co * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_start, (size_t)n_recordings * sizeof(long long)));
+    if (total) CUF(cudaMemcpy(d_ev, events_yxt, (size_t)total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUF(cudaMemcpy(d_cnt, cnt.data(), (size_t)n_recordings * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUF(cudaMemcpy(d_start, rec_offsets, (size_t)n_recordings * sizeof(long long), cudaMemcpyHostToDevice));
+    CUF(cudaMemset(d_co, 0, n_co * sizeof(int32_t)));
+    SplitParams p;
+    p.events = d_ev; p.rec_start = d_start; p.counts = d_cnt; p.chunk_off = d_co; p.n_chunks = d_nc;
+    p.size = batch_event_size; p.usec = batch_event_usec;
+    k_split_batches<<<n_recordings, kThreads>>>(p);
+    CUF(cudaGetLastError());
+    CUF(cudaDeviceSynchronize());
+    CUF(cudaMemcpy(chunk_offsets_out, d_co, n_co * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUF(cudaMemcpy(n_chunks_out, d_nc, (size_t)n_recordings * sizeof(int32_t), cudaMemcpyDeviceToHost));
+#undef CUF
+    cleanup();
+    return AEC_OK;
+}
+
+// Raw recordings -> detections without leaving the device (f3 + f1 in front of the path): decode + the
+// runner's transform (k_ndata_decode), batching (k_split_batches), then one step per batch index with every stream
+// consuming its own batch (k_chunk_ranges feeds the surface kernel), reset on the first batch only (runner.py:64,101).
+extern "C" int aec_net_run_ndata(aec_net *n, const uint8_t *raw, const long long *byte_offsets, int zero_base_ts, int crop, int new_h,
+                                 int new_w, int batch_event_size, int batch_event_usec, int reset_first, float *head_out,
+                                 int32_t *steps_out, int32_t *event_counts_out, void *cuda_stream)
+{
+    NEED_FINAL(n);
+    if (!byte_offsets) return fail(AEC_EINVAL, "run_ndata: byte_offsets is NULL");
+    if (batch_event_usec <= 0 && batch_event_size < 1) return fail(AEC_EINVAL, "run_ndata: batch_event_size must be >= 1");
+    const int R = n->S;
+    if (byte_offsets[0] != 0) return fail(AEC_EINVAL, "run_ndata: byte_offsets[0] must be 0");
+    for (int r = 0; r < R; ++r)
+        if (byte_offsets[r + 1] < byte_offsets[r] || byte_offsets[r + 1] % 5)
+            return fail(AEC_EINVAL, "run_ndata: recording %d is not a whole number of 5-byte records", r);
+    const long long total_bytes = byte_offsets[R];
+    if (total_bytes > 0 && !raw) return fail(AEC_EINVAL, "run_ndata: NULL recordings");
+    const long long n_ev = total_bytes / 5;
+    if (n_ev + 2LL * R >= (1LL << 31)) return fail(AEC_EINVAL, "run_ndata: too many events");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint8_t *d_raw = nullptr;
+    long long *d_off = nullptr, *d_start = nullptr;
+    int32_t *d_ev = nullptr, *d_cnt = nullptr, *d_co = nullptr, *d_nc = nullptr, *d_begin = nullptr, *d_end = nullptr;
+    auto cleanup = [&]() {
+        n->ev_ends = nullptr;
+        cudaFree(d_raw); cudaFree(d_off); cudaFree(d_start); cudaFree(d_ev); cudaFree(d_cnt); cudaFree(d_co); cudaFree(d_nc);
+        cudaFree(d_begin); cudaFree(d_end);
+    };
+#define CUF(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { cleanup(); return fail(AEC_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    const size_t n_co = (size_t)n_ev + 2 * (size_t)R;
+    std::vector<long long> start(R);
+    for (int r = 0; r < R; ++r) start[r] = byte_offsets[r] / 5;
+    CUF(cudaMalloc(&d_raw, std::max<long long>(total_bytes, 1)));
+    CUF(cudaMalloc(&d_off, ((size_t)R + 1) * sizeof(long long)));
+    CUF(cudaMalloc(&d_start, (size_t)R * sizeof(long long)));
+    CUF(cudaMalloc(&d_ev, std::max<long long>(n_ev, 1) * 3 * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_cnt, (size_t)R * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_nc, (size_t)R * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_co, n_co * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_begin, (size_t)R * sizeof(int32_t)));
+    CUF(cudaMalloc(&d_end, (size_t)R * sizeof(int32_t)));
+    if (total_bytes) CUF(cudaMemcpyAsync(d_raw, raw, (size_t)total_bytes, cudaMemcpyHostToDevice, st));
+    CUF(cudaMemcpyAsync(d_off, byte_offsets, ((size_t)R + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUF(cudaMemcpyAsync(d_start, start.data(), (size_t)R * sizeof(long long), cudaMemcpyHostToDevice, st));
+    NdataParams dp;
+    dp.raw = d_raw; dp.byte_off = d_off; dp.events = d_ev; dp.polarity = nullptr; dp.counts = d_cnt;
+    dp.zero_base = zero_base_ts; dp.crop = crop; dp.new_h = new_h; dp.new_w = new_w;
+    k_ndata_decode<<<R, kThreads, 0, st>>>(dp);
+    CUF(cudaGetLastError());
+    SplitParams sp;
+    sp.events = d_ev; sp.rec_start = d_start; sp.counts = d_cnt; sp.chunk_off = d_co; sp.n_chunks = d_nc;
+    sp.size = batch_event_size; sp.usec = batch_event_usec;
+    k_split_batches<<<R, kThreads, 0, st>>>(sp);
+    CUF(cudaGetLastError());
+    n->launches += 2;
+    std::vector<int32_t> nc(R);
+    CUF(cudaMemcpyAsync(nc.data(), d_nc, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (event_counts_out) CUF(cudaMemcpyAsync(event_counts_out, d_cnt, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUF(cudaStreamSynchronize(st));              // the number of steps is data dependent: one read-back of R integers
+    int steps = 0;
+    for (int r = 0; r < R; ++r) steps = std::max(steps, (int)nc[r]);
+    int rc = AEC_OK;
+    if (reset_first && (rc = reset_streams(n, nullptr, st))) { cleanup(); return rc; }
+    n->ev_ends = d_end;
+    for (int b = 0; b < steps && rc == AEC_OK; ++b) {
+        k_chunk_ranges<<<(R + kThreads - 1) / kThreads, kThreads, 0, st>>>(d_start, d_co, d_nc, b, R, d_begin, d_end);
+        if ((rc = launch_check(n, "k_chunk_ranges"))) break;
+        rc = aec_net_step_device(n, d_ev, d_begin, (int)n_ev, cuda_stream);
+    }
+    if (rc == AEC_OK && head_out)
+        if (cudaMemcpyAsync(head_out, n->head_last ? n->head_last : n->head, (size_t)n->S * n->head_per_stream * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = fail(AEC_ECUDA, "run_ndata: copying the head failed");
+    if (rc == AEC_OK) rc = check_err_flag(n, st);
+    else cudaStreamSynchronize(st);
+    if (steps_out) *steps_out = steps;
+#undef CUF
+    cleanup();
+    return rc;
 }
 
 extern "C" int aec_decode_ndata(int device, const uint8_t *raw, const long long *byte_offsets, int n_recordings, int zero_base_ts,

@@ -127,6 +127,73 @@ __global__ void __launch_bounds__(kThreads) k_ndata_decode(NdataParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batching of a recording's events into steps.   src/libs/runner.py:65-72 (intended semantics)
+//   count mode (usec == 0): n = max(ceil(N / size), 1) chunks as np.array_split(events, n) cuts them: the first N % n
+//                           chunks hold N / n + 1 events, the others N / n;
+//   time mode  (usec > 0):  bins = arange(0, ts[N-1], usec); id_j = digitize(ts_j, bins) = min(ts_j / usec + 1, len(bins))
+//                           (0 for a negative ts); a new chunk starts wherever id_j != id_(j-1).
+// One CTA per recording; the chunk offsets (relative to the recording's first event) go to
+// chunk_off[rec_start[r] + 2 r + k], k = 0 .. n_chunks[r] (a recording of N events has at most max(N, 1) chunks).
+// ---------------------------------------------------------------------------------------------
+struct SplitParams {
+    const int32_t *events;        // (y, x, ts) triples
+    const long long *rec_start;   // [R] index of the recording's first event
+    const int32_t *counts;        // [R] events in the recording
+    int32_t *chunk_off;           // [total + 2 R]
+    int32_t *n_chunks;            // [R]
+    int size, usec;
+};
+
+__global__ void __launch_bounds__(kThreads) k_split_batches(SplitParams p)
+{
+    __shared__ int scratch[9];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int N = p.counts[r];
+    const long long e0 = p.rec_start[r];
+    int32_t *out = p.chunk_off + e0 + 2 * (long long)r;
+    if (p.usec <= 0) {
+        const int n = max((N + p.size - 1) / p.size, 1);
+        const int q = N / n, rem = N - q * n;
+        for (int i = tid; i <= n; i += kThreads) out[i] = i * q + min(i, rem);
+        if (tid == 0) p.n_chunks[r] = n;
+        return;
+    }
+    if (N == 0) {
+        if (tid == 0) { out[0] = 0; out[1] = 0; p.n_chunks[r] = 1; }
+        return;
+    }
+    const int32_t *ts = p.events + 3 * e0 + 2;
+    const int last = ts[3 * (long long)(N - 1)];
+    const int nb = last > 0 ? (last + p.usec - 1) / p.usec : 0;
+    auto bin = [&](int t) { return t < 0 ? 0 : min(t / p.usec + 1, nb); };
+    if (tid == 0) out[0] = 0;
+    int cuts_before = 0;
+    for (int base = 1; base < N; base += kThreads) {
+        const int j = base + tid;
+        const bool cut = j < N && bin(ts[3 * (long long)j]) != bin(ts[3 * (long long)(j - 1)]);
+        int tot;
+        const int pos = block_excl_scan(cut ? 1 : 0, scratch, &tot);
+        if (cut) out[1 + cuts_before + pos] = j;
+        cuts_before += tot;
+    }
+    if (tid == 0) { out[1 + cuts_before] = N; p.n_chunks[r] = cuts_before + 1; }
+}
+
+// Event range of every stream for step `b` of a batched run: stream s consumes chunk b of recording s (nothing once its
+// recording is exhausted).  begin / end index the packed event array.
+__global__ void __launch_bounds__(kThreads) k_chunk_ranges(const long long *rec_start, const int32_t *chunk_off, const int32_t *n_chunks,
+                                                           int b, int R, int32_t *begin, int32_t *end)
+{
+    const int s = blockIdx.x * kThreads + threadIdx.x;
+    if (s >= R) return;
+    const long long e0 = rec_start[s];
+    const int32_t *co = chunk_off + e0 + 2 * (long long)s;
+    const bool live = b < n_chunks[s];
+    begin[s] = (int32_t)(e0 + (live ? co[b] : 0));
+    end[s] = (int32_t)(e0 + (live ? co[b + 1] : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
 // YOLO decode.   src/libs/viz.py:27-46 (convert_bboxes, sqrt = True), :131-148,165 (draw_bboxes)
 //   head [S][gh][gw][C + 5B]: C class scores, then B x (x, y, w, h, conf);
 //   box  x = ((bx + col) / gw) * w_img,  y = ((by + row) / gh) * h_img,  w = bw^2 * w_img,  h = bh^2 * h_img

@@ -210,7 +210,8 @@ struct IntegrateParams {
     uint32_t *front;        // [S][H*Ww]
     uint32_t *alive;        // [S][H*Ww] pixels with S > 0 after the step (the layer's non-zero-rate bitmap)
     const int32_t *events;  // [total][3] (y,x,ts)
-    const int32_t *offsets; // [S+1]
+    const int32_t *offsets; // [S+1] (or [S] first event of every stream when `ends` is given)
+    const int32_t *ends;    // null: stream s owns events offsets[s] .. offsets[s+1]; else offsets[s] .. ends[s] (batched recordings)
     int *layer_counts;      // [n_layers] work-list counters, zeroed here for the step
     int *err_flag;
     int n_layers;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
     if (s == 0 && tid < p.n_layers) p.layer_counts[tid] = 0;
 
     const int e0 = p.offsets[s];
-    int n = p.offsets[s + 1] - e0;
+    int n = (p.ends ? p.ends[s] : p.offsets[s + 1]) - e0;
     uint32_t *front = p.front + (long long)s * nbm;
     if (n > p.max_events) {
         if (tid == 0) atomicOr(p.err_flag, 2);

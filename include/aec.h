@@ -251,6 +251,34 @@ int aec_decode_ndata(int device, const uint8_t *raw, const long long *byte_offse
                      int crop, int new_h, int new_w, int32_t *events_yxt_out, int32_t *polarity_out, int32_t *counts_out);
 
 /*
+ * The batching step of the runner on the device (src/libs/runner.py:65-72 with the intended semantics
+ * of SURVEY Q5): splits every recording's events into the chunks one network step consumes.
+ *   batch_event_usec == 0: max(ceil(N / batch_event_size), 1) chunks cut like np.array_split (runner.py:71-72);
+ *   batch_event_usec  > 0: fixed-duration bins, np.digitize(ts, arange(0, ts[-1], usec)), a new chunk where the bin
+ *                          changes (runner.py:66-69).
+ * events_yxt (HOST, int32 [total][3]) holds the recordings back to back, recording r = events
+ * [rec_offsets[r], rec_offsets[r+1]).  Outputs (HOST): n_chunks_out[r], and the chunk boundaries relative to the
+ * recording's first event at chunk_offsets_out[rec_offsets[r] + 2 r + k], k = 0 .. n_chunks_out[r]
+ * (chunk_offsets_out has total + 2 * n_recordings entries).  Stand-alone; synchronises the device.
+ */
+int aec_split_batches(int device, const int32_t *events_yxt, const long long *rec_offsets, int n_recordings,
+                      int batch_event_size, int batch_event_usec, int32_t *chunk_offsets_out, int32_t *n_chunks_out);
+
+/*
+ * Raw recordings -> detections without a host round trip: what Runner.run does for one sample per stream
+ * (runner.py:55-101) - data_transform (aec_decode_ndata's kernel), the batching above, then graph(events_batch, reset)
+ * for every batch with reset only on the first (runner.py:64,101) - entirely on the device.  `raw` / `byte_offsets`
+ * (HOST) hold exactly n_streams recordings, recording s feeds stream s; a stream whose recording has fewer batches
+ * idles for the remaining steps.  head_out (HOST, may be NULL) receives the head after the last step
+ * ([n_streams][H_last][W_last][C_last]); steps_out the number of steps run (the largest batch count);
+ * event_counts_out (may be NULL) the events kept per recording.  Returns AEC_EEVENTS if a batch exceeded
+ * max_events_per_step or an event fell outside the frame.  Synchronises `cuda_stream`.
+ */
+int aec_net_run_ndata(aec_net *net, const uint8_t *raw, const long long *byte_offsets, int zero_base_ts, int crop, int new_h,
+                      int new_w, int batch_event_size, int batch_event_usec, int reset_first, float *head_out,
+                      int32_t *steps_out, int32_t *event_counts_out, void *cuda_stream);
+
+/*
  * Measurement helper for the leak sweep's roofline.  out8 = { 16-byte groups of the conv rate maps holding a
  * non-zero rate, all such groups, conv-map elements at sites whose non-zero-rate bit is set (live elements),
  * all conv-map elements, the same two for the pool layers' (Fp, Ap) copies, and the live conv / pool-copy

@@ -95,3 +95,81 @@ def test_decode_head_known_answer():
     assert np.allclose(boxes[0, i], [(0.5 + 0) / 2 * 200, (0.25 + 1) / 2 * 100, 0.25 * 200, 0.25 * 100])
     assert conf[0, i] == np.float32(0.9) and valid[0, i] and label[0, i] == 1
     assert valid.sum() == 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f1 on the device: batching of a sample into steps (runner.py:65-72) and recordings -> detections without a host
+# round trip
+# ---------------------------------------------------------------------------------------------------------------
+def _samples(rng):
+    """Ragged samples: empty, one event, fewer than a batch, exact multiples, long; timestamps with repeats and gaps."""
+    out = []
+    for n in [0, 1, 3, 39, 40, 41, 80, 130, 257, 5000]:
+        ts = np.cumsum(rng.integers(0, 60, n)) if n else np.zeros(0, np.int64)
+        if n > 50:
+            ts[n // 2:] += 7000                                  # a long silence: empty duration bins in between
+        out.append(np.stack([rng.integers(0, 16, n), rng.integers(0, 24, n), ts], axis=-1).astype(np.int32))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,usec", [(40, None), (1, None), (7, None), (100000, None), (40, 500), (40, 1), (40, 100000), (40, 64)])
+def test_device_batching_equals_the_runner_split(size, usec):
+    from async_ev_cnn_b200.frontend import split_batches
+    from async_ev_cnn_b200.runner import split_event_batches
+    samples = _samples(np.random.default_rng(5))
+    got = split_batches(samples, batch_event_size=size, batch_event_usec=usec)
+    for ev, b in zip(samples, got):
+        if len(ev) == 0 and usec is not None:
+            assert b.tolist() == [0, 0]                          # the reference indexes events[-1] here and raises; one empty batch
+            continue
+        want = split_event_batches(ev, size, usec)
+        bounds = np.concatenate([[0], np.cumsum([len(c) for c in want])]).astype(np.int32)
+        assert np.array_equal(b, bounds), "N=%d size=%s usec=%s" % (len(ev), size, usec)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,usec", [(60, None), (60, 4000)])
+def test_recordings_to_detections_on_the_device_equal_the_python_loop(size, usec):
+    """aec_net_run_ndata (decode + transform + batching + steps, all on the device) == decoding, splitting and feeding the
+    chunks from Python (the runner's loop), bit for bit; streams with fewer batches idle."""
+    import async_ev_cnn_b200 as P
+    from oracle import frontend as F
+    from async_ev_cnn_b200.engine import EventNetCuda
+    from async_ev_cnn_b200.frontend import decode_ndata, run_recordings
+    from async_ev_cnn_b200.runner import split_event_batches
+    layers = "conv1=3,3,1,4 pool1=2,2 conv2=3,3,4,8 pool2=2,2 conv3=1,1,8,6"
+    h, w, S = 32, 48, 4
+    rng = np.random.default_rng(3)
+    recs = []
+    for n in [900, 0, 333, 1500]:
+        x = rng.integers(0, 60, n).astype(np.int32)
+        y = rng.integers(0, 44, n).astype(np.int32)
+        ts = np.sort(rng.integers(0, 1 << 15, n)).astype(np.int32)
+        recs.append(F.encode_ndata(x, y, ts, rng.integers(0, 2, n).astype(np.int32)))
+    wts = P.xavier_weights(layers, seed=2)
+    a = EventNetCuda(h, w, layers, wts, 1e-4, 0.1, "SAME", n_streams=S, max_events_per_step=4096)
+    b = EventNetCuda(h, w, layers, wts, 1e-4, 0.1, "SAME", n_streams=S, max_events_per_step=4096)
+    heads, steps, kept = run_recordings(a, recs, crop_to=(h, w), batch_event_size=size, batch_event_usec=usec)
+    evs = decode_ndata(recs, zero_base_ts=True, crop_to=(h, w))
+    assert [len(e) for e in evs] == kept.tolist()
+    chunks = [split_event_batches(e, size, usec) if len(e) else [e] for e in evs]
+    assert steps == max(len(c) for c in chunks)
+    want = None
+    b.reset()
+    for t in range(steps):
+        per = [c[t] if t < len(c) and len(c[t]) else None for c in chunks]
+        want = b.step(per).copy()
+    assert np.array_equal(heads, want)
+    for li in range(len(a.names)):
+        for s in range(S):
+            sa, sb = a.state(li, s), b.state(li, s)
+            for k in sa:
+                assert np.array_equal(sa[k], sb[k]), "layer %s stream %d %s" % (a.names[li], s, k)
+    # a second call without reset continues the streams; with reset it reproduces the first
+    heads2, _, _ = run_recordings(a, recs, crop_to=(h, w), batch_event_size=size, batch_event_usec=usec, reset=True)
+    assert np.array_equal(heads2, heads)
+    with pytest.raises(ValueError):
+        run_recordings(a, recs[:2])
+    a.close()
+    b.close()
