@@ -6,6 +6,7 @@
 #include "../../include/aec.h"
 #include "aec_kernels.cuh"
 #include "aec_tc.cuh"
+#include "aec_rt.cuh"
 #include "aec_frontend.cuh"
 
 #include <algorithm>
@@ -62,6 +63,13 @@ struct HostLayer {
     int KB = 0, Mrows = 0, Mch = 0, rep = 1, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
     bool tc_fast_decode = false;   // which site-decoder variant of k_conv_eval_tc the layer runs (fixed at finalize)
     bool tc_sm = false;            // sites-as-M form of the kernel (Cout <= 64, multiple of 4): aec_tc.cuh
+    // row-tile form (aec_rt.cuh) of a sites-as-M layer: units of rt_R output rows x one x segment instead of single sites
+    bool rt = false;
+    int rt_R = 0, rt_sw_shift = 0, rt_SEG = 0, rt_nxg = 0, rt_CB = 0, rt_ncb = 0, rt_P = 0, rt_xst = 0, rt_wst = 0;
+    size_t rt_xtile = 0, rt_wtile = 0, rt_smem = 0;
+    std::vector<float> h_rtimg;
+    float *rtimg = nullptr;
+    uint32_t *nset = nullptr;      // [S][H*Ww] exact work set of the step (written by the frontier kernel)
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
@@ -286,6 +294,65 @@ static void build_tc_image(HostLayer &l, bool prev_is_map, const float *kernel_h
                     }
 }
 
+// Row-tile form (aec_rt.cuh): for a sites-as-M layer with a real window (kh*kw > 1) whose input pixel splits into 64- or
+// 128-byte channel blocks.  AEC_RT=0 keeps the gathered kernel (A/B runs).
+static void build_rt_image(HostLayer &l, const float *kernel_hwio)
+{
+    const char *e = getenv("AEC_RT");
+    if (!l.tc || !l.tc_sm || l.kh * l.kw <= 1 || l.kw > 8 || (e && atoi(e) == 0)) return;
+    if (!(l.Cin == 16 || l.Cin % 32 == 0)) return;
+    l.rt_CB = l.Cin == 16 ? 16 : 32;
+    l.rt_ncb = l.Cin / l.rt_CB;
+    const int row_bytes = l.rt_CB * 4;
+    const int need = l.W + l.kw - 1;                 // slot width a whole output row needs (its input columns + the window's halo)
+    if (need <= 64) {
+        int sw = 16;
+        l.rt_sw_shift = 4;
+        while (sw < need) { sw <<= 1; ++l.rt_sw_shift; }
+        l.rt_R = 128 / sw;
+        l.rt_SEG = l.W;
+        l.rt_nxg = 1;
+    } else {
+        l.rt_sw_shift = 7;
+        l.rt_R = 1;
+        l.rt_SEG = 128 - (l.kw - 1);
+        l.rt_nxg = (l.W + l.rt_SEG - 1) / l.rt_SEG;
+    }
+    const int nyg = (l.H + l.rt_R - 1) / l.rt_R;
+    if ((long long)nyg * l.rt_nxg > 32LL * kThreads) return;          // emit_units: at most 32 units per thread of the frontier CTA
+    l.rt_P = 128 + l.kw - 1;
+    if ((l.rt_P * (l.rt_CB / 4) + rt::kRtProdThreads - 1) / rt::kRtProdThreads > rt::kRtMaxPairs) return;
+    const int cpad = l.Mrows;                                          // channels rounded up to 16 (sites-as-M)
+    l.rt_xtile = ((size_t)l.rt_P * row_bytes + 1023) / 1024 * 1024;
+    l.rt_wtile = (size_t)2 * cpad * row_bytes;
+    const size_t budget = 208 * 1024;
+    l.rt_xst = 4 * l.rt_xtile * 3 + 3 * l.rt_wtile <= budget ? 3 : 2;
+    l.rt_wst = (int)std::min<size_t>(rt::kRtMaxWStages, (budget - (size_t)l.rt_xst * 4 * l.rt_xtile) / l.rt_wtile);
+    if (l.rt_wst < 2) return;
+    l.rt_smem = (size_t)l.rt_xst * 4 * l.rt_xtile + (size_t)l.rt_wst * l.rt_wtile + 1024;
+    l.rt = true;
+    // image: [(ky*kw + kx)*ncb + cb][row: W_hi of channel r (r < Cpad), then W_lo][CB floats], 16-byte chunks swizzled on the
+    // address bits like the site tiles (tiles are multiples of 1024 bytes)
+    const size_t tile_floats = l.rt_wtile / 4;
+    l.h_rtimg.assign((size_t)l.kh * l.kw * l.rt_ncb * tile_floats, 0.f);
+    for (int ky = 0; ky < l.kh; ++ky)
+        for (int kx = 0; kx < l.kw; ++kx)
+            for (int cb = 0; cb < l.rt_ncb; ++cb) {
+                float *tile = l.h_rtimg.data() + (size_t)((ky * l.kw + kx) * l.rt_ncb + cb) * tile_floats;
+                for (int r = 0; r < 2 * cpad; ++r)
+                    for (int j = 0; j < l.rt_CB; ++j) {
+                        const int col = r % cpad;
+                        const int k = (ky * l.kw + kx) * l.Cin + cb * l.rt_CB + j;
+                        const float w = col < l.C ? kernel_hwio[(size_t)k * l.C + col] : 0.f;
+                        float hi, lo;
+                        split_tf32_host(w, &hi, &lo);
+                        uint32_t lin = (uint32_t)r * row_bytes + (uint32_t)j * 4;
+                        lin ^= ((lin >> 7) & (row_bytes == 128 ? 7u : 3u)) << 4;
+                        tile[lin / 4] = r < cpad ? hi : lo;
+                    }
+            }
+}
+
 extern "C" int aec_net_add_conv(aec_net *n, int k_h, int k_w, int c_in, int c_out, const float *kernel_hwio,
                                 const float *bias, int stride, float alpha, int padding)
 {
@@ -327,6 +394,7 @@ extern "C" int aec_net_add_conv(aec_net *n, int k_h, int k_w, int c_in, int c_ou
     for (int c = 0; c < c_out; ++c) l.h_b[c] = bias[c];
     { int rc = set_site_code(n, l); if (rc) return rc; }
     build_tc_image(l, p.type != AEC_LAYER_INTEGRATION, kernel_hwio);
+    build_rt_image(l, kernel_hwio);
     n->L.push_back(std::move(l));
     return (int)n->L.size() - 1;
 }
@@ -499,9 +567,34 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     return rc ? rc : prof_mark(n, st);
 }
 
-static int run_conv_eval(aec_net *n, int li, cudaStream_t st)
+// Row-tile evaluation: only inside the fused step, whose frontier kernel wrote the unit list and the work-set bitmap.
+static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
 {
     HostLayer &l = n->L[li];
+    const Src src = make_src(n, li - 1);
+    rt::RtParams p;
+    memset(&p, 0, sizeof p);
+    p.units = l.sites; p.counter = n->counts + li; p.site_counter = n->counts + 32 + li;
+    p.accum_sites = n->accum + li; p.accum_units = n->accum + 32 + li;
+    p.srcF = src.F; p.a_minus_f = (const char *)src.A - (const char *)src.F; p.zero_f = (const char *)src.F - kMapGuardFloats * 4;
+    p.src_stride = src.fstride; p.alpha = src.alpha;
+    p.Cin = src.C; p.Hin = src.H; p.Win = src.W;
+    p.wimg = l.rtimg; p.bias = l.bias; p.F = l.F; p.A = l.A; p.fstride = l.fstride; p.nset = l.nset;
+    p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.Cpad = l.Mrows;
+    p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
+    p.CB = l.rt_CB; p.ncb = l.rt_ncb; p.row_bytes = l.rt_CB * 4;
+    p.R = l.rt_R; p.sw_shift = l.rt_sw_shift; p.SEG = l.rt_SEG; p.code = l.code; p.P = l.rt_P;
+    p.x_tile_bytes = (uint32_t)l.rt_xtile; p.w_tile_bytes = (uint32_t)l.rt_wtile; p.x_stages = l.rt_xst; p.w_stages = l.rt_wst;
+    p.debug = n->tc_debug;
+    rt::k_conv_rows<<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
+    int rc = launch_check(n, "k_conv_rows");
+    return rc ? rc : prof_mark(n, st);
+}
+
+static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = false)
+{
+    HostLayer &l = n->L[li];
+    if (l.rt && fused_step) return run_conv_rows(n, li, st);
     if (l.tc) return run_conv_eval_tc(n, li, st);
     static const bool no_stencil = getenv("AEC_CONV_PATH") && strcmp(getenv("AEC_CONV_PATH"), "simt") == 0;
     if (n->L[li - 1].type == AEC_LAYER_INTEGRATION && l.C % 4 == 0 && l.C <= kStencilMaxC && l.kh * l.kw <= kStencilMaxK && !no_stencil) {
@@ -579,9 +672,9 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     return run_pool_eval(n, li, st);
 }
 
-static int run_eval(aec_net *n, int li, cudaStream_t st)
+static int run_eval(aec_net *n, int li, cudaStream_t st)      // evaluation of layer li inside the fused step
 {
-    return n->L[li].type == AEC_LAYER_CONV ? run_conv_eval(n, li, st) : run_pool_eval(n, li, st);
+    return n->L[li].type == AEC_LAYER_CONV ? run_conv_eval(n, li, st, true) : run_pool_eval(n, li, st);
 }
 
 static int run_frontier_skip(aec_net *n, cudaStream_t st)
@@ -697,6 +790,12 @@ extern "C" int aec_net_finalize(aec_net *n)
                 CU(cudaMemcpy(l.wimg, l.h_wimg.data(), l.h_wimg.size() * 4, cudaMemcpyHostToDevice));
                 l.h_wimg.clear(); l.h_wimg.shrink_to_fit();
             }
+            if (l.rt) {
+                if ((rc = dev_alloc(n, &l.rtimg, l.h_rtimg.size(), false))) return rc;
+                CU(cudaMemcpy(l.rtimg, l.h_rtimg.data(), l.h_rtimg.size() * 4, cudaMemcpyHostToDevice));
+                l.h_rtimg.clear(); l.h_rtimg.shrink_to_fit();
+                if ((rc = dev_alloc(n, &l.nset, S * bm, true))) return rc;
+            }
         } else if (l.type == AEC_LAYER_POOL) {
             if ((rc = dev_alloc(n, &l.idx, S * l.fstride, true))) return rc;
             if ((rc = dev_alloc(n, &l.flags, S * bm, true))) return rc;
@@ -720,8 +819,8 @@ extern "C" int aec_net_finalize(aec_net *n)
     for (auto &l : n->L)
         if (l.type != AEC_LAYER_INTEGRATION) n->view_elems = std::max(n->view_elems, (size_t)l.H * l.W * l.C);
     if ((rc = dev_alloc(n, &n->view, 4 * n->view_elems, false))) return rc;
-    if ((rc = dev_alloc(n, &n->counts, 32, false))) return rc;
-    if ((rc = dev_alloc(n, &n->accum, 32, false))) return rc;
+    if ((rc = dev_alloc(n, &n->counts, 64, false))) return rc;      // [l]: work-list entries of layer l; [32 + l]: work-set sites of a row-tile layer
+    if ((rc = dev_alloc(n, &n->accum, 64, false))) return rc;       // [l]: sites evaluated; [32 + l]: row-tile units evaluated; [31]: scratch
     if ((rc = dev_alloc(n, &n->err_flag, 1, false))) return rc;
     if ((rc = dev_alloc(n, &n->off_dev, S + 1, false))) return rc;
     const HostLayer &last = n->L.back();
@@ -739,6 +838,7 @@ extern "C" int aec_net_finalize(aec_net *n)
             f.type = l.type; f.Hin = pv.H; f.Win = pv.W; f.WwIn = pv.Ww; f.H = l.H; f.W = l.W; f.Ww = l.Ww;
             f.kh = l.kh; f.kw = l.kw; f.pad_t = l.pad_t; f.pad_l = l.pad_l; f.stride = l.stride; f.code = l.code;
             f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.skip = l.skip; f.sites = l.sites; f.counter = n->counts + li;
+            f.rt_rows = l.rt ? l.rt_R : 0; f.rt_seg = l.rt_SEG; f.rt_nxg = l.rt_nxg; f.nset = l.nset; f.counter2 = n->counts + 32 + li;
             mw = std::max(mw, std::max(pv.H * pv.Ww, std::max(pv.H * l.Ww, l.H * l.Ww)));
         }
         n->front_max_words = mw;
@@ -811,6 +911,21 @@ extern "C" int aec_net_finalize(aec_net *n)
                     return fail(AEC_EINVAL, "tensor-core conv kernel needs %zu + %zu bytes of shared memory", tc_max, (size_t)fa.sharedSizeBytes);
             }
         }
+        size_t rt_max = 0;
+        for (auto &l : n->L)
+            if (l.rt) rt_max = std::max(rt_max, l.rt_smem);
+        if (rt_max) {
+            const void *fn = (const void *)rt::k_conv_rows;
+            cudaFuncAttributes fa;
+            CU(cudaFuncGetAttributes(&fa, fn));
+            if (rt_max + fa.sharedSizeBytes > 227 * 1024)
+                return fail(AEC_EINVAL, "row-tile conv kernel needs %zu + %zu bytes of shared memory", rt_max, (size_t)fa.sharedSizeBytes);
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_max));
+            const int pool = fa.numRegs * tc::kTcThreads;
+            const int want = 128 * tc::kRegsEpi + 128 * tc::kRegsCtl + 384 * tc::kRegsProd;
+            if (want > pool || fa.numRegs > tc::kRegsProd || fa.numRegs < tc::kRegsEpi)
+                return fail(AEC_EINVAL, "row-tile conv kernel was built with %d registers/thread; the role split needs %d of %d", fa.numRegs, want, pool);
+        }
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));
         n->conv_eval_blocks[0] = std::max(1, b) * n->num_sms;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<32, 4, 4, 16>, kThreads, 0));
@@ -841,8 +956,8 @@ extern "C" int aec_net_finalize(aec_net *n)
             CU(cudaMemsetAsync(l.flags, 0, (size_t)l.H * l.Ww * 4, st));
         }
     }
-    CU(cudaMemsetAsync(n->accum, 0, 32 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(n->counts, 0, 32 * sizeof(int), st));
+    CU(cudaMemsetAsync(n->accum, 0, 64 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(n->counts, 0, 64 * sizeof(int), st));
     if ((rc = reset_streams(n, nullptr, st))) return rc;
     CU(cudaStreamSynchronize(st));
     n->finalized = true;
@@ -1211,15 +1326,26 @@ extern "C" int aec_net_read_counters(aec_net *n, unsigned long long *sites, int 
 {
     NEED_FINAL(n);
     CU(cudaDeviceSynchronize());
-    unsigned long long tmp[32];
+    unsigned long long tmp[64];
     CU(cudaMemcpy(tmp, n->accum, sizeof tmp, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n_layers && i < 32; ++i)
+    for (int i = 0; i < n_layers && i < 31; ++i)
         if (sites) sites[i] = i < (int)n->L.size() ? tmp[i] : 0ULL;
     if (steps) *steps = n->steps;
     if (reset) {
         CU(cudaMemset(n->accum, 0, sizeof tmp));
         n->steps = 0;
     }
+    return AEC_OK;
+}
+
+extern "C" int aec_net_read_unit_counters(aec_net *n, unsigned long long *units, int n_layers)
+{
+    NEED_FINAL(n);
+    if (!units) return fail(AEC_EINVAL, "read_unit_counters: units is NULL");
+    CU(cudaDeviceSynchronize());
+    unsigned long long tmp[64];
+    CU(cudaMemcpy(tmp, n->accum, sizeof tmp, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_layers && i < 31; ++i) units[i] = (i < (int)n->L.size() && n->L[i].rt) ? tmp[32 + i] : 0ULL;
     return AEC_OK;
 }
 
@@ -1324,7 +1450,15 @@ extern "C" int aec_net_tc_geometry(const aec_net *n, int layer, long long *out8)
     out8[1] = tc::kUnitSites;
     out8[5] = l.m_tiles;
     out8[3] = k8;
-    if (l.tc_sm) {
+    if (l.rt) {
+        // per unit (128 tile sites): kh * ncb stages x kw taps x CB/8 K steps x {value, rate} x {N = 2 Cpad, N = Cpad}
+        const long long steps8 = (long long)l.kh * l.rt_ncb * l.kw * (l.rt_CB / 8);
+        out8[3] = steps8;
+        out8[4] = 4;
+        out8[2] = steps8 * 2LL * (2LL * 128 * (2 * l.Mrows) * 8 + 2LL * 128 * l.Mrows * 8);
+        out8[6] = 3;
+        out8[7] = 1;                                               // units are counted by aec_net_read_unit_counters
+    } else if (l.tc_sm) {
         out8[4] = 4;                                               // {value, rate} x {X_hi.[W_hi;W_lo] (N = 2 Cpad), X_lo.W_hi (N = Cpad)}
         out8[2] = k8 * 2LL * (2LL * 128 * (2 * l.Mrows) * 8 + 2LL * 128 * l.Mrows * 8);
         out8[6] = 2;

@@ -195,6 +195,46 @@ __device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int Ww, ui
     }
 }
 
+// Row-tile layers: emits one entry per unit (rt_rows output rows x one x segment) that holds a work-set bit,
+// entry = base_id | row group << sh_y | segment, in (row group, segment) order.
+__device__ __forceinline__ void emit_units(const uint32_t *bm, int H, int W, int Ww, int rows, int seg, int nxg, uint32_t base_id, int sh_y,
+                                           uint32_t *units, int *counter, int *scratch)
+{
+    const int nyg = (H + rows - 1) / rows;
+    const int n_units = nyg * nxg;
+    const int per = (n_units + kThreads - 1) / kThreads;
+    const int u0 = threadIdx.x * per, u1 = min(n_units, u0 + per);
+    auto any = [&](int u) {
+        const int yg = u / nxg, xg = u - yg * nxg;
+        const int c0 = xg * seg, c1 = min(W, c0 + seg);
+        const int w0 = c0 >> 5, w1 = (c1 - 1) >> 5;
+        for (int y = yg * rows; y < min(H, (yg + 1) * rows); ++y)
+            for (int w = w0; w <= w1; ++w) {
+                uint32_t m = 0xffffffffu;
+                if (w == w0) m &= 0xffffffffu << (c0 & 31);
+                if (w == w1 && (c1 & 31)) m &= (1u << (c1 & 31)) - 1u;
+                if (bm[y * Ww + w] & m) return true;
+            }
+        return false;
+    };
+    uint32_t hits = 0u;                     // per <= 32 units per thread for any frame the bitmaps of which fit in shared memory
+    int cnt = 0;
+    for (int u = u0; u < u1; ++u)
+        if (any(u)) { hits |= 1u << (u - u0); ++cnt; }
+    int total;
+    int off = block_excl_scan(cnt, scratch, &total);
+    __shared__ int s_ubase;
+    if (threadIdx.x == 0) s_ubase = total > 0 ? atomicAdd(counter, total) : 0;
+    __syncthreads();
+    off += s_ubase;
+    while (hits) {
+        const int b = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int u = u0 + b, yg = u / nxg;
+        units[off++] = base_id | ((uint32_t)yg << sh_y) | (uint32_t)(u - yg * nxg);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: integration surface.  One CTA per stream.   integration.py:53-91
 //   t_L = max ts; delta = (t_L - t_prev) * leak; S = max(S - delta, 0);
@@ -234,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
     const int tid = threadIdx.x;
     const int HW = p.H * p.W;
     const int nbm = p.H * p.Ww;
-    if (s == 0 && tid < p.n_layers) p.layer_counts[tid] = 0;
+    if (s == 0 && tid < p.n_layers) { p.layer_counts[tid] = 0; p.layer_counts[32 + tid] = 0; }   // [32 + l]: work-set sites of a row-tile layer
 
     const int e0 = p.offsets[s];
     int n = (p.ends ? p.ends[s] : p.offsets[s + 1]) - e0;
@@ -703,6 +743,9 @@ struct FrontLayer {
     int Hin, Win, WwIn, H, W, Ww;
     int kh, kw, pad_t, pad_l, stride;
     SiteCode code;
+    int rt_rows, rt_seg, rt_nxg;  // row-tile conv layer (aec_rt.cuh): rows per unit (0 = the layer takes a site list), sites per x segment, segments per row
+    uint32_t *nset;               // row-tile layer: [S][H*Ww] copy of the exact work set (the evaluation stores only there)
+    int *counter2;                // row-tile layer: number of work-set sites (statistics)
     uint32_t *front, *signchg, *flags, *nzr;
     uint32_t *skip;               // [S][H*Ww] written by k_frontier_skip: a subset of this step's work set, known before the leak sweep
     uint32_t *sites;
@@ -827,7 +870,18 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
             for (int i = tid; i < nout; i += kThreads) bufA[i] = N[i];
             __syncthreads();
         }
-        emit_sites(N, L.H, L.Ww, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.sites, L.counter, scratch);
+        if (L.type == 1 && L.rt_rows > 0) {
+            // row-tile conv layer: the evaluation needs the work set itself (it stores only there) and one entry per active unit
+            uint32_t *ns = L.nset + (long long)s * nout;
+            int cnt = 0;
+            for (int i = tid; i < nout; i += kThreads) { const uint32_t w = N[i]; ns[i] = w; cnt += __popc(w); }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            if ((tid & 31) == 0 && cnt) atomicAdd(L.counter2, cnt);
+            emit_units(N, L.H, L.W, L.Ww, L.rt_rows, L.rt_seg, L.rt_nxg, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.sites, L.counter, scratch);
+        } else {
+            emit_sites(N, L.H, L.Ww, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.sites, L.counter, scratch);
+        }
         __syncthreads();
         for (int i = tid; i < nout; i += kThreads) bufB[i] = Z[i];
         __syncthreads();

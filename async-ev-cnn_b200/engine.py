@@ -329,8 +329,15 @@ class EventNetCuda:
             return None
         return {"unit_sites": int(buf[1]), "mma_flops_per_unit": float(buf[2]), "m_groups": 1, "k8_steps": int(buf[3]),
                 "mma_per_kstep": int(buf[4]), "weight_tiles": int(buf[5]),
+                "units_counted": bool(buf[7]),
                 "kernel": ("k_conv_eval_tc<simple decode, weights-as-M>", "k_conv_eval_tc<batched decode, weights-as-M>",
-                           "k_conv_eval_tc<sites-as-M>")[int(buf[6])]}
+                           "k_conv_eval_tc<sites-as-M>", "k_conv_rows (row tiles, sites-as-M)")[int(buf[6])]}
+
+    def unit_counters(self):
+        """Work units evaluated per layer by the row-tile kernel since the last counters(reset=True)."""
+        units = np.zeros(len(self.names), np.uint64)
+        N.check(self._lib.aec_net_read_unit_counters(self._h, _ptr(units), len(self.names)))
+        return units
 
     TC_TIMING_SLOTS = ("mma_total", "mma_wait_acc", "mma_wait_sites", "mma_wait_weights", "prod_total", "prod_wait_siteinfo",
                        "prod_wait_stage", "epi_total", "epi_wait_acc", "epi_wait_siteinfo", "load_total", "load_wait", "ctas", "units",

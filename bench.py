@@ -282,7 +282,7 @@ def tf32_peak(peaks, sm_mhz):
         return bf16 / 2.0, ("MEASURED_PEAKS.json bf16_tflops_sustained / 2" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s bf16 / 2")
 
 
-def layer_table(net, prof, sites_per_step, streams, tf32_pk, hbm_pk):
+def layer_table(net, prof, sites_per_step, streams, tf32_pk, hbm_pk, units_per_step=None):
     """Per-launch table of one step: ms, work, useful TFLOP/s (conv) and algorithmic GB/s against the measured peaks."""
     rows = {}
     for i, nm in enumerate(net.names):
@@ -302,7 +302,9 @@ def layer_table(net, prof, sites_per_step, streams, tf32_pk, hbm_pk):
                 row["useful_TFLOPs"] = round(fl / (ms * 1e-3) / 1e12, 2)
                 row["useful_frac_of_tf32_peak"] = round(fl / (ms * 1e-3) / 1e12 / tf32_pk, 4)
                 if tc is not None:
-                    issued = tc["mma_flops_per_unit"] * np.ceil(n / tc["unit_sites"]) * tc["m_groups"]
+                    n_units = float(units_per_step[i]) if (tc.get("units_counted") and units_per_step is not None) else np.ceil(n / tc["unit_sites"])
+                    row["units_of_128_sites"] = round(n_units, 1)
+                    issued = tc["mma_flops_per_unit"] * n_units * tc["m_groups"]
                     row["issued_TFLOPs"] = round(issued / (ms * 1e-3) / 1e12, 2)
                     row["issued_frac_of_tf32_peak"] = round(issued / (ms * 1e-3) / 1e12 / tf32_pk, 4)
                     row["kernel"] = tc["kernel"]
@@ -355,6 +357,7 @@ def run_leg(torch, P, EventNetCuda, name, layers, h, w, S, B, kind, preroll, K, 
     torch.cuda.synchronize()
     clocks = sampler.stop(w0, time.perf_counter())
     ms = e0.elapsed_time(e1) / K
+    units_per_step = net.unit_counters().astype(np.float64) / K
     sites, _ = net.counters(reset=True)
     sites_per_step = sites.astype(np.float64) / K
     sw = net.sweep_stats()
@@ -367,7 +370,7 @@ def run_leg(torch, P, EventNetCuda, name, layers, h, w, S, B, kind, preroll, K, 
     hbm_pk = float(peaks.get("hbm_gbs", 6650.0))
     tf_pk, _ = tf32_peak(peaks, clocks.get("sm_mhz"))
     ab = algorithmic_bytes(net, sites_per_step, sw, S, B, h, w)
-    table = layer_table(net, prof, sites_per_step, S, tf_pk, hbm_pk)
+    table = layer_table(net, prof, sites_per_step, S, tf_pk, hbm_pk, units_per_step)
     top = max(prof.items(), key=lambda kv: kv[1])
     out = {"value": S * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "preroll_steps": preroll,
            "streams_per_gpu": S, "batch_event_size": B, "stream_kind": kind, "frame": [h, w], "event_rate_per_us": rate,
@@ -514,6 +517,7 @@ def native_arm(args):
     clocks = sampler.stop(w0, w1)
     ms_total = e0.elapsed_time(e1)
     launches = net.launch_count() - launches0
+    units_per_step = net.unit_counters().astype(np.float64) / K
     sites, _ = net.counters(reset=True)
     sites_per_step = sites.astype(np.float64) / K
     if world > 1:
@@ -554,9 +558,9 @@ def native_arm(args):
     tf_pk, tf_src = tf32_peak(peaks, clocks.get("sm_mhz"))
     tc_tflops = fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     n_tc = max(1, len(tc_layers))
-    table = layer_table(net, prof, sites_per_step, S, tf_pk, peak)
+    table = layer_table(net, prof, sites_per_step, S, tf_pk, peak, units_per_step)
     issued = sum(table[net.names[i]].get("issued_TFLOPs", 0.0) * table[net.names[i]]["ms"] for i in tc_layers)
-    roofline = {"bound": "tensor", "kernel": "k_conv_eval_tc", "achieved": tc_tflops, "peak": tf_pk, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": "k_conv_rows / k_conv_eval_tc (tcgen05 conv re-evaluation, one launch per conv layer)", "achieved": tc_tflops, "peak": tf_pk, "unit": "TFLOP/s",
                 "frac": tc_tflops / tf_pk, "traffic": None, "peak_source": tf_src,
                 "precision": "3xTF32 (two or three tcgen05.mma.kind::tf32 per product for fp32-grade results): `achieved` counts "
                              "USEFUL FLOPs (2 x sites x {value, rate} x K x Cout); `issued` what the tensor pipe was asked to do, "

@@ -301,9 +301,16 @@ int aec_net_tc_timing(aec_net *net, int enable, int layer, unsigned long long *o
  * roofline table.  out8 = { 1 if the layer runs on the tcgen05 kernel else 0, sites per work unit,
  * tensor FLOPs ISSUED per unit over all weight tiles (every tcgen05.mma counted as 2*M*N*K with its padding rows
  * and all split-precision products), 8-wide K steps, MMAs per K step and weight tile, weight tiles, kernel variant
- * id, 0 }.  Returns 0, or a negative code for a bad layer index.
+ * id, 1 if units are counted by aec_net_read_unit_counters (row-tile kernel) }.  Returns 0, or a negative code for a bad layer index.
  */
 int aec_net_tc_geometry(const aec_net *net, int layer, long long *out8);
+
+/*
+ * Measurement helper: work units evaluated per layer since the last counter reset, for the layers that run on the
+ * row-tile kernel (aec_net_tc_geometry out8[7] == 1; a unit = 128 tile sites, work-set sites and gaps alike); 0 for
+ * every other layer.  Reset together with aec_net_read_counters(reset = 1).
+ */
+int aec_net_read_unit_counters(aec_net *net, unsigned long long *units, int n_layers);
 
 /* Number of kernels this library has launched since creation of `net` (for bench `gpu_launches`). */
 unsigned long long aec_net_launch_count(const aec_net *net);

@@ -281,6 +281,46 @@ def test_unusual_shapes_against_live_oracle_exact(layers, h, w):
     net.close()
 
 
+@pytest.mark.parametrize("layers,h,w,padding", [
+    # conv2: 16 -> 32 channels on a 24-wide map: 4 output rows per unit (slot 32); conv3: 32 -> 8 on 12 columns: 8 rows per unit
+    ("conv1=3,3,1,16 pool1=2,2 conv2=3,3,16,32 pool2=2,2 conv3=3,3,32,8", 32, 48, "SAME"),
+    # rows wider than one tile: x segments of 126 sites (272 columns = 3 segments), 64-byte and 128-byte tile rows
+    ("conv1=3,3,1,16 conv2=3,3,16,16 conv3=3,3,16,32 conv4=3,3,32,12", 10, 272, "SAME"),
+    # VALID padding and a 5x5 window (tile rows 0..131, taps read the tile from 0..4 rows further on)
+    ("conv1=3,3,1,16 conv2=5,5,16,32 pool1=2,2 conv3=3,3,32,64", 30, 70, "VALID"),
+    # two channel blocks per pixel (Cin = 64)
+    ("conv1=3,3,1,16 conv2=3,3,16,64 conv3=3,3,64,16", 20, 40, "SAME"),
+])
+def test_row_tile_conv_layers_exact(layers, h, w, padding):
+    """Layers that take the row-tile kernel (aec_rt.cuh: Cin = 16 or a multiple of 32, Cout <= 64) on exactly
+    representable nets: every map, frontier, argmax and flag bit-equal to the oracle, several streams with idle steps."""
+    S, steps = 3, 40
+    wts = P.xavier_weights(layers, seed=21, exact=True)
+    evs = P.synthetic_events("edge", S, steps, 30, h, w, seed=23, dt_int=(1, 5))
+    net = EventNetCuda(h, w, layers, wts, 1.0 / 64, 0.5, padding, n_streams=S)
+    assert any(g is not None and "k_conv_rows" in g["kernel"] for g in (net.tc_geometry(i) for i in range(1, len(net.names)))), \
+        "no layer of this net took the row-tile kernel"
+    oracles = [OracleEventNet(h, w, layers, wts, 1.0 / 64, 0.5, padding) for _ in range(S)]
+    for t in range(steps):
+        per = [evs[s, t] if (s + t) % 6 else None for s in range(S)]
+        heads = net.step(per)
+        for s in range(S):
+            if per[s] is not None:
+                assert np.array_equal(heads[s], oracles[s].step(per[s])), "step %d stream %d head" % (t, s)
+        if t % 8 == 7 or t == steps - 1:
+            for s in range(S):
+                oa = OracleAdapter(oracles[s])
+                for i in range(len(net.names)):
+                    so, sc = oa.state(i), net.state(i, s)
+                    for key in so:
+                        assert np.array_equal(sc[key], so[key]), "step %d stream %d layer %s %s" % (t, s, net.names[i], key)
+                    if per[s] is not None:
+                        assert np.array_equal(net.frontier(i, s), oa.frontier(i))
+    units = net.unit_counters()
+    assert units.sum() > 0
+    net.close()
+
+
 def test_long_run_through_pixel_deaths_exact():
     """300 steps with a leak that kills a pixel within a few steps: the surface kernel walks only the pixels alive
     after the previous step (its alive bitmap), so births, deaths and re-births must keep that bitmap exact."""
