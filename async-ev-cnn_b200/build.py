@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libaec_b200.so")
 SOURCES = [os.path.join(CSRC, "aec.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "aec_kernels.cuh"), os.path.join(CSRC, "aec_tc.cuh"), os.path.join(CSRC, "aec_frontend.cuh"), os.path.join(os.path.dirname(PKG), "include", "aec.h")]
+DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join(os.path.dirname(PKG), "include", "aec.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

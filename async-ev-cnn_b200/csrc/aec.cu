@@ -67,6 +67,8 @@ struct HostLayer {
     bool rt = false;
     int rt_R = 0, rt_sw_shift = 0, rt_SEG = 0, rt_nxg = 0, rt_CB = 0, rt_ncb = 0, rt_P = 0, rt_xst = 0, rt_wst = 0;
     size_t rt_xtile = 0, rt_wtile = 0, rt_smem = 0;
+    bool rt_wres = false;          // weights resident in shared memory for the whole launch
+    int rt_groups = 3;             // producer groups
     std::vector<float> h_rtimg;
     float *rtimg = nullptr;
     uint32_t *nset = nullptr;      // [S][H*Ww] exact work set of the step (written by the frontier kernel)
@@ -321,14 +323,25 @@ static void build_rt_image(HostLayer &l, const float *kernel_hwio)
     const int nyg = (l.H + l.rt_R - 1) / l.rt_R;
     if ((long long)nyg * l.rt_nxg > 32LL * kThreads) return;          // emit_units: at most 32 units per thread of the frontier CTA
     l.rt_P = 128 + l.kw - 1;
-    if ((l.rt_P * (l.rt_CB / 4) + rt::kRtProdThreads - 1) / rt::kRtProdThreads > rt::kRtMaxPairs) return;
+    const int n_pairs = l.rt_P * (l.rt_CB / 4);
+    l.rt_groups = (n_pairs + 127) / 128 <= rt::kRtMaxPairs ? 3 : 2;      // producer groups of 4 or 6 warps (aec_rt.cuh)
+    if ((n_pairs + (12 / l.rt_groups) * 32 - 1) / ((12 / l.rt_groups) * 32) > rt::kRtMaxPairs) return;
     const int cpad = l.Mrows;                                          // channels rounded up to 16 (sites-as-M)
     l.rt_xtile = ((size_t)l.rt_P * row_bytes + 1023) / 1024 * 1024;
     l.rt_wtile = (size_t)2 * cpad * row_bytes;
-    const size_t budget = 208 * 1024;
-    l.rt_xst = 4 * l.rt_xtile * 3 + 3 * l.rt_wtile <= budget ? 3 : 2;
-    l.rt_wst = (int)std::min<size_t>(rt::kRtMaxWStages, (budget - (size_t)l.rt_xst * 4 * l.rt_xtile) / l.rt_wtile);
-    if (l.rt_wst < 2) return;
+    const size_t budget = 217 * 1024;                // 227 KB per CTA minus the alignment slack and the kernel's static shared memory
+    const size_t all_w = (size_t)l.kh * l.kw * l.rt_ncb * l.rt_wtile;
+    l.rt_wres = all_w <= 48 * 1024 && all_w + 2 * 4 * l.rt_xtile <= budget;   // resident weights (aec_rt.cuh): no streaming latency
+    if (l.rt_wres) {
+        l.rt_wst = l.kh * l.kw * l.rt_ncb;
+        l.rt_xst = all_w + 3 * 4 * l.rt_xtile <= budget ? 3 : 2;
+    } else {
+        l.rt_xst = 4 * l.rt_xtile * 3 + (size_t)(l.kw + 2) * l.rt_wtile <= budget ? 3 : 2;
+        l.rt_wst = (int)std::min<size_t>(rt::kRtMaxWStages, (budget - (size_t)l.rt_xst * 4 * l.rt_xtile) / l.rt_wtile);
+        if (l.rt_wst < l.kw + 1) return;             // the kw tiles of a kernel row plus at least one prefetched tile of the next
+    }
+    if (l.rt_xst < l.rt_groups) l.rt_groups = l.rt_xst;              // a group per site stage at most
+    if ((n_pairs + (12 / l.rt_groups) * 32 - 1) / ((12 / l.rt_groups) * 32) > rt::kRtMaxPairs) return;
     l.rt_smem = (size_t)l.rt_xst * 4 * l.rt_xtile + (size_t)l.rt_wst * l.rt_wtile + 1024;
     l.rt = true;
     // image: [(ky*kw + kx)*ncb + cb][row: W_hi of channel r (r < Cpad), then W_lo][CB floats], 16-byte chunks swizzled on the
@@ -584,9 +597,15 @@ static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
     p.CB = l.rt_CB; p.ncb = l.rt_ncb; p.row_bytes = l.rt_CB * 4;
     p.R = l.rt_R; p.sw_shift = l.rt_sw_shift; p.SEG = l.rt_SEG; p.code = l.code; p.P = l.rt_P;
-    p.x_tile_bytes = (uint32_t)l.rt_xtile; p.w_tile_bytes = (uint32_t)l.rt_wtile; p.x_stages = l.rt_xst; p.w_stages = l.rt_wst;
+    p.x_tile_bytes = (uint32_t)l.rt_xtile; p.w_tile_bytes = (uint32_t)l.rt_wtile; p.x_stages = l.rt_xst; p.w_stages = l.rt_wst; p.w_resident = l.rt_wres ? 1 : 0;
     p.debug = n->tc_debug;
-    rt::k_conv_rows<<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
+    p.prod_groups = l.rt_groups;
+    p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
+    const bool staged = l.C > 32;          // epilogue stores through the per-warp transpose buffer (aec_rt.cuh)
+    if (l.rt_CB == 32 && staged) rt::k_conv_rows<32, true><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
+    else if (l.rt_CB == 32) rt::k_conv_rows<32, false><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
+    else if (staged) rt::k_conv_rows<16, true><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
+    else rt::k_conv_rows<16, false><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_rows");
     return rc ? rc : prof_mark(n, st);
 }
@@ -914,8 +933,10 @@ extern "C" int aec_net_finalize(aec_net *n)
         size_t rt_max = 0;
         for (auto &l : n->L)
             if (l.rt) rt_max = std::max(rt_max, l.rt_smem);
-        if (rt_max) {
-            const void *fn = (const void *)rt::k_conv_rows;
+        const void *rt_variants[4] = {(const void *)rt::k_conv_rows<16, false>, (const void *)rt::k_conv_rows<16, true>,
+                                      (const void *)rt::k_conv_rows<32, false>, (const void *)rt::k_conv_rows<32, true>};
+        for (const void *fn : rt_variants) {
+            if (!rt_max) break;
             cudaFuncAttributes fa;
             CU(cudaFuncGetAttributes(&fa, fn));
             if (rt_max + fa.sharedSizeBytes > 227 * 1024)

@@ -34,7 +34,7 @@ constexpr int kRtMaxXStages = 3;
 constexpr int kRtMaxWStages = 6;
 constexpr int kRtRing = 4;            // unit-info buffers
 constexpr int kRtProdThreads = kGroups * kGroupThreads;   // 384
-constexpr int kRtMaxPairs = 3;        // (tile row, 16-byte chunk) pairs per producer thread and stage
+constexpr int kRtMaxPairs = 6;        // (tile row, 16-byte chunk) pairs per producer thread and stage
 
 struct RtParams {
     const uint32_t *units;      // work list: stream << sh_s | row group << sh_y | x segment
@@ -61,8 +61,11 @@ struct RtParams {
     int P;                      // tile rows written per stage (128 + kw - 1)
     uint32_t x_tile_bytes;      // one of the four tiles of a stage (V_hi, V_lo, R_hi, R_lo), multiple of 1024
     uint32_t w_tile_bytes;      // 2 * Cpad * row_bytes
-    int x_stages, w_stages;
+    int x_stages, w_stages;     // w_stages: weight tile slots; w_resident: every tile has its own slot, loaded once per CTA
+    int w_resident;
     int debug;
+    int prod_groups;            // the 12 producer warps work as 2 or 3 groups; group g fills the stages q = g, g + G, ...
+    unsigned long long *timing; // null, or the 16 role cycle counters of aec_net_tc_timing (TcTimingSlot)
 };
 
 struct __align__(16) UnitInfo {
@@ -84,13 +87,22 @@ __device__ __forceinline__ uint32_t rt_off(int t, int c, int row_bytes)
 }
 
 // Dynamic shared memory: [pad to 1024][w_stages x w_tile][x_stages x 4 x x_tile].
+// kCB = channels per block (16: 64-byte tile rows, SWIZZLE_64B; 32: 128-byte rows, SWIZZLE_128B) is a template parameter so
+// that the MMA issue loop and the producers' index arithmetic are compile-time shapes; kStaged selects the epilogue's store path.
+template <int kCB, bool kStaged>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_constant__ RtParams p)
 {
     extern __shared__ unsigned char rt_smem_raw[];
+    // Weights: a layer whose kh*kw*ncb tiles fit (conv2: 36 KB) keeps them RESIDENT - loaded once per CTA, bar_w_full[0] - because a
+    // streamed tile travels commit -> loader -> L2 -> shared memory -> gatekeeper in ~4 k cycles (measured, profiles/r2_summary.md)
+    // and a ring of D slots therefore sustains D tiles per 4 k cycles only: less than the tensor core consumes when a tile feeds
+    // 8 MMAs.  Larger layers stream tile by tile through bar_w_full / bar_w_empty (conv3: 16 MMAs per tile, 5 slots).
     __shared__ __align__(8) uint64_t bar_x_full[kRtMaxXStages], bar_x_empty[kRtMaxXStages], bar_w_full[kRtMaxWStages], bar_w_empty[kRtMaxWStages];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_u_full[kRtRing], bar_u_free[kRtRing];
     __shared__ uint32_t s_tmem;
     __shared__ UnitInfo s_unit[kRtRing];
+    __shared__ __align__(16) float s_etile[kEpiWarps][32 * 16];       // epilogue: one 32 sites x 16 channels chunk per warp (transpose buffer)
+    __shared__ long long s_edst[kEpiWarps][32];                       // epilogue: destination byte offset of the warp's sites (-1: no store)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total_units = __shfl_sync(0xffffffffu, *p.counter, 0);
@@ -106,10 +118,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
 
     if (tid == 0) {
         for (int i = 0; i < p.x_stages; ++i) {
-            mbar_init(smem_u32(&bar_x_full[i]), kRtProdThreads / 32);      // one arrival per producer warp
+            mbar_init(smem_u32(&bar_x_full[i]), 12 / p.prod_groups);      // one arrival per warp of the producer group that fills the stage
             mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
-        for (int i = 0; i < p.w_stages; ++i) {
+        for (int i = 0; i < (p.w_resident ? 1 : p.w_stages); ++i) {
             mbar_init(smem_u32(&bar_w_full[i]), 1);
             mbar_init(smem_u32(&bar_w_empty[i]), 1);
         }
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
         }
         for (int i = 0; i < kRtRing; ++i) {
             mbar_init(smem_u32(&bar_u_full[i]), 1);
-            mbar_init(smem_u32(&bar_u_free[i]), kEpiWarps * 32 + kRtProdThreads);   // epilogue and producers both read the unit info
+            mbar_init(smem_u32(&bar_u_free[i]), kEpiWarps * 32);          // the epilogue is the last role to finish a unit: its release is enough
         }
         fence_barrier_init();
     }
@@ -134,6 +146,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
     const int n_units_cta = (total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_st = p.kh * p.ncb;                       // stages per unit: (kernel row, channel block)
     const int SW = 1 << p.sw_shift;
+    const bool timing = p.timing != nullptr;
 
     if (warp < kEpiWarps) {
         // ===================== epilogue: one thread = one site of the tile =====================
@@ -144,22 +157,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
         const int cpad = p.Cpad;
         const int nch = (p.C + 15) >> 4;
         const int total = 2 * nch;
+        long long tw_acc = 0, tw_si = 0;
+        const long long t_begin = timing ? clock64() : 0;
+        // Whether a site is in the layer's work set (a site outside it keeps its leaked value: no store) is one bit of a
+        // bitmap in global memory: the word of the NEXT unit is fetched while the current one is written out, so that its
+        // latency is off the unit's critical path.
+        auto fetch = [&](int ul_, UnitInfo &u, uint32_t &word) {
+            const int buf = ul_ % kRtRing;
+            timed_wait(smem_u32(&bar_u_full[buf]), (uint32_t)(ul_ / kRtRing) & 1u, timing, tw_si);
+            u = s_unit[buf];
+            const int oy = u.y0 + rr, ox = u.x0 + x;
+            u.valid = rr < p.R && x < p.SEG && oy < p.H && ox < p.W;
+            word = u.valid ? __ldg(p.nset + ((long long)u.s * p.H + oy) * p.Ww + (ox >> 5)) : 0u;
+        };
+        UnitInfo u, u_next;
+        uint32_t word, word_next = 0u;
+        u_next.s = u_next.y0 = u_next.x0 = u_next.valid = 0;
+        fetch(0, u, word);
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int buf = ul % kRtRing, ab = ul & 1;
-            mbar_wait(smem_u32(&bar_u_full[buf]), (uint32_t)(ul / kRtRing) & 1u);
-            const UnitInfo u = s_unit[buf];
-            // is this site in the layer's work set?  (a site outside it keeps its leaked value: no store)
+            if (ul + 1 < n_units_cta) fetch(ul + 1, u_next, word_next);
             long long dst = -1;
             {
                 const int oy = u.y0 + rr, ox = u.x0 + x;
-                if (u.valid && rr < p.R && x < p.SEG && oy < p.H && ox < p.W) {
-                    const uint32_t word = __ldg(p.nset + ((long long)u.s * p.H + oy) * p.Ww + (ox >> 5));
-                    if ((word >> (ox & 31)) & 1u) dst = ((long long)u.s * p.fstride + ((long long)oy * p.W + ox) * p.C) * 4;
-                }
+                if (u.valid && ((word >> (ox & 31)) & 1u)) dst = ((long long)u.s * p.fstride + ((long long)oy * p.W + ox) * p.C) * 4;
             }
-            mbar_arrive(smem_u32(&bar_u_free[buf]));
-            mbar_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul >> 1) & 1u);
+            timed_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul >> 1) & 1u, timing, tw_acc);
             tc_fence_after();
+            mbar_arrive(smem_u32(&bar_u_free[buf]));          // every stage of this unit is complete: no role needs its slot any more
             const bool site_ok = dst >= 0 && !(p.debug & 8);
             const uint32_t tbase = lane_addr + (uint32_t)(ab * 4 * cpad);
             uint32_t ra[16], rb[16], rc[16], rd[16];
@@ -169,24 +194,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
                 tmem_ld16(ta, hi);
                 tmem_ld16(ta + (uint32_t)cpad, lo);
             };
+            // The accumulator comes out site-per-lane (16 channels = 64 bytes per thread and chunk); stored like that, one store
+            // instruction is 32 separate 16-byte requests to 32 different lines, and the requests - not the bytes - bounded the
+            // epilogue (5.9 k cycles per unit of conv2 against 4.1 k of MMAs).  So each warp transposes its 32 x 16 chunk through a
+            // private 2 KB buffer: lane l then stores piece l % 4 of sites l / 4 + 8 i, four lanes = one contiguous 64-byte run.
+            // Buffer rows are 64 bytes; the 16-byte piece index is XORed with (row >> 1) & 3 so that neither the writes (lane =
+            // row) nor the reads (4 lanes per row) conflict.
+            // Measured (profiles/r2_summary.md): the transpose pays for 64 channels (conv3 0.56 -> 0.50 ms: 8 chunks per unit) and
+            // costs for 32 (conv2 0.77 -> 0.87 ms: its two extra warp barriers and the shared-memory round trip per chunk outweigh
+            // the better requests), so it is used for C > 32 only.
+            constexpr bool staged = kStaged;                 // host: C > 32
+            if (staged) {
+                s_edst[warp][lane] = site_ok ? dst : -1;
+                __syncwarp();
+            }
             auto emit = [&](int ci, const uint32_t(&hi)[16], const uint32_t(&lo)[16]) {
                 const int map = ci >= nch ? 1 : 0, c0 = (ci - map * nch) << 4;
-                if (!site_ok) return;
-                char *const out = (char *)(map ? p.A : p.F) + dst + (long long)c0 * 4;
+                if (!staged) {
+                    if (!site_ok) return;
+                    char *const out = (char *)(map ? p.A : p.F) + dst + (long long)c0 * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (c0 + 4 * q >= p.C) break;
+                        float4 o;
+                        o.x = __fadd_rn(__uint_as_float(hi[4 * q + 0]), __uint_as_float(lo[4 * q + 0]));
+                        o.y = __fadd_rn(__uint_as_float(hi[4 * q + 1]), __uint_as_float(lo[4 * q + 1]));
+                        o.z = __fadd_rn(__uint_as_float(hi[4 * q + 2]), __uint_as_float(lo[4 * q + 2]));
+                        o.w = __fadd_rn(__uint_as_float(hi[4 * q + 3]), __uint_as_float(lo[4 * q + 3]));
+                        if (!map) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + 4 * q));
+                            o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+                        }
+                        *reinterpret_cast<float4 *>(out + 16 * q) = o;
+                    }
+                    return;
+                }
+                const uint32_t wbase = smem_u32(&s_etile[warp][0]);
+                const uint32_t sw = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (c0 + 4 * q >= p.C) break;
                     float4 o;
                     o.x = __fadd_rn(__uint_as_float(hi[4 * q + 0]), __uint_as_float(lo[4 * q + 0]));
                     o.y = __fadd_rn(__uint_as_float(hi[4 * q + 1]), __uint_as_float(lo[4 * q + 1]));
                     o.z = __fadd_rn(__uint_as_float(hi[4 * q + 2]), __uint_as_float(lo[4 * q + 2]));
                     o.w = __fadd_rn(__uint_as_float(hi[4 * q + 3]), __uint_as_float(lo[4 * q + 3]));
-                    if (!map) {
+                    if (!map && c0 + 4 * q < p.C) {
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + 4 * q));
                         o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
                     }
-                    *reinterpret_cast<float4 *>(out + 16 * q) = o;
+                    sts128(wbase + (uint32_t)lane * 64u + (((uint32_t)q ^ sw) << 4), o);
                 }
+                __syncwarp();
+                const int piece = lane & 3;
+                char *const outm = (char *)(map ? p.A : p.F) + (long long)(c0 + 4 * piece) * 4;
+                const bool piece_ok = c0 + 4 * piece < p.C;                  // C % 4 == 0: whole 16-byte pieces only
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (lane >> 2) + 8 * i;
+                    const long long d = s_edst[warp][row];
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(wbase + (uint32_t)row * 64u + (((uint32_t)piece ^ (uint32_t)((row >> 1) & 3)) << 4)));
+                    if (d >= 0 && piece_ok) *reinterpret_cast<float4 *>(outm + d) = v;
+                }
+                __syncwarp();
             };
             issue(0, ra, rb);
 #pragma unroll 1
@@ -200,87 +271,141 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bar_acc_empty[ab]));
+            u = u_next;
+            word = word_next;
+        }
+        if (timing && tid == 0) {
+            atomicAdd(p.timing + kTEpiTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTEpiWaitAcc, (unsigned long long)tw_acc);
+            atomicAdd(p.timing + kTEpiWaitSite, (unsigned long long)tw_si);
+            atomicAdd(p.timing + kTCtas, 1ULL);
+            atomicAdd(p.timing + kTUnits, (unsigned long long)n_units_cta);
         }
     } else if (warp < kProdWarp0) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
       if (warp == kMmaWarp) {
         // ===================== MMA issuer (no mbarrier waits here: see aec_tc.cuh) =====================
+        // The issue loop is kept as lean as the compiler allows: one thread issues an instruction every few cycles, so a
+        // descriptor rebuilt from an address per MMA (shift, mask, or: ~6 uniform-datapath instructions) makes the ISSUE
+        // slower than the 64-cycle MMA it feeds (measured: ~104 cycles per MMA).  Descriptors are therefore kept as 32-bit
+        // low words (start address >> 4, with the constant LBO bit) that advance by plain adds; the high word is constant.
         const uint32_t idesc_cat = make_idesc_tf32(2 * p.Cpad), idesc_hi = make_idesc_tf32(p.Cpad);
         const uint32_t x_base = smem_u32(smem_x), w_base = smem_u32(smem_w);
-        const int ks_n = p.CB / 8;
-        uint32_t qx = 0, qw = 0;
+        const uint64_t desc_top = make_desc_rt(0u, kCB * 4) & 0xffffffff00000000ull;
+        const uint32_t tile16 = p.x_tile_bytes >> 4, wtile16 = p.w_tile_bytes >> 4, xstage16 = x_stage_bytes >> 4;
+        const uint32_t x0_lo = ((x_base & 0x3ffffu) >> 4) | (1u << 16), w0_lo = ((w_base & 0x3ffffu) >> 4) | (1u << 16);
+        constexpr int ks_n = kCB / 8;
+        constexpr uint32_t row16 = (uint32_t)(kCB * 4) >> 4;
+        uint32_t sx = 0, sw = 0, qp = 0;
+        long long tw_gate = 0;
+        const long long t_begin = timing ? clock64() : 0;
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int ab = ul & 1;
             const uint32_t dv = tmem_base + (uint32_t)(ab * 4 * p.Cpad), dr = dv + (uint32_t)(2 * p.Cpad);
-            for (int st = 0; st < n_st; ++st, ++qx) {
-                const uint32_t sx = qx % (uint32_t)p.x_stages;
-                const uint32_t xs = x_base + sx * x_stage_bytes;
-                for (int kx = 0; kx < p.kw; ++kx, ++qw) {
-                    const uint32_t sw = qw % (uint32_t)p.w_stages;
-                    const uint32_t wt = w_base + sw * p.w_tile_bytes;
-                    const uint32_t xa = xs + (uint32_t)kx * (uint32_t)p.row_bytes;     // tap kx: the tile read from kx rows further on
-                    asm volatile("bar.sync %0, 64;" ::"r"(1u + (qw & 7u)) : "memory");     // ids 1..8: the gatekeeper is at most w_stages <= 6 passes ahead
-                    tc_fence_after();
-                    if (elect_one()) {
+            for (int st = 0; st < n_st; ++st, ++qp) {
+                // one pass per stage = kernel row: all kw taps behind one hand-off
+                const uint32_t xv = x0_lo + sx * xstage16;
+                const int ky = st / p.ncb, cb = st - ky * p.ncb;
+                const long long t0 = timing ? clock64() : 0;
+                asm volatile("bar.sync %0, 64;" ::"r"(1u + (qp & 7u)) : "memory");
+                if (timing) tw_gate += clock64() - t0;
+                tc_fence_after();
+                if (elect_one()) {
+                    uint32_t xa = xv, swl = sw;
+                    for (int kx = 0; kx < p.kw; ++kx, xa += row16) {         // tap kx: the tile read from kx rows further on
+                        const uint32_t slot = p.w_resident ? (uint32_t)((ky * p.kw + kx) * p.ncb + cb) : swl;
+                        const uint32_t wl = w0_lo + slot * wtile16;
                         if (!(p.debug & 4)) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint32_t ko = (uint32_t)ks * 32u;
-                                const uint64_t dw = make_desc_rt(wt + ko, p.row_bytes);
-                                const uint64_t dvh = make_desc_rt(xa + ko, p.row_bytes), dvl = make_desc_rt(xa + p.x_tile_bytes + ko, p.row_bytes);
-                                const uint64_t drh = make_desc_rt(xa + 2u * p.x_tile_bytes + ko, p.row_bytes), drl = make_desc_rt(xa + 3u * p.x_tile_bytes + ko, p.row_bytes);
-                                if (ks >= ks_n) break;
+                            for (int ks = 0; ks < ks_n; ++ks) {
+                                const uint64_t dw = desc_top | (uint64_t)(wl + 2u * ks);
                                 const uint32_t acc = (st | kx | ks) != 0 ? 1u : 0u;
-                                mma_tf32(dv, dvh, dw, idesc_cat, acc);
-                                mma_tf32(dr, drh, dw, idesc_cat, acc);
-                                mma_tf32(dv, dvl, dw, idesc_hi, 1u);
-                                mma_tf32(dr, drl, dw, idesc_hi, 1u);
+                                mma_tf32(dv, desc_top | (uint64_t)(xa + 2u * ks), dw, idesc_cat, acc);
+                                mma_tf32(dr, desc_top | (uint64_t)(xa + 2u * tile16 + 2u * ks), dw, idesc_cat, acc);
+                                mma_tf32(dv, desc_top | (uint64_t)(xa + tile16 + 2u * ks), dw, idesc_hi, 1u);
+                                mma_tf32(dr, desc_top | (uint64_t)(xa + 3u * tile16 + 2u * ks), dw, idesc_hi, 1u);
                             }
                         }
-                        mma_commit(smem_u32(&bar_w_empty[sw]));
-                        if (kx == p.kw - 1) mma_commit(smem_u32(&bar_x_empty[sx]));
-                        if (kx == p.kw - 1 && st == n_st - 1) mma_commit(smem_u32(&bar_acc_full[ab]));
+                        if (!p.w_resident) {
+                            mma_commit(smem_u32(&bar_w_empty[swl]));         // this tap's weight slot may be refilled
+                            if (++swl == (uint32_t)p.w_stages) swl = 0;
+                        }
                     }
-                    __syncwarp();
+                    mma_commit(smem_u32(&bar_x_empty[sx]));
+                    if (st == n_st - 1) mma_commit(smem_u32(&bar_acc_full[ab]));
                 }
+                if (!p.w_resident) {
+                    sw += (uint32_t)p.kw;
+                    if (sw >= (uint32_t)p.w_stages) sw -= (uint32_t)p.w_stages;
+                }
+                __syncwarp();
+                if (++sx == (uint32_t)p.x_stages) sx = 0;
             }
+        }
+        if (timing && lane == 0) {
+            atomicAdd(p.timing + kTMmaTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTMmaWaitX, (unsigned long long)tw_gate);
         }
       } else if (warp == kGateWarp) {
         // ===================== gatekeeper: every wait of the MMA warp =====================
         uint32_t qx = 0, qw = 0;
+        long long tw_acc = 0, tw_x = 0, tw_w = 0;
+        if (p.w_resident) timed_wait(smem_u32(&bar_w_full[0]), 0u, timing, tw_w);       // the resident weights have landed
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int ab = ul & 1;
             const uint32_t ua = (uint32_t)(ul >> 1);
-            if (ua > 0) mbar_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u);
+            if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);
             for (int st = 0; st < n_st; ++st, ++qx) {
                 const uint32_t sx = qx % (uint32_t)p.x_stages;
                 const uint32_t px = (qx / (uint32_t)p.x_stages) & 1u;
-                for (int kx = 0; kx < p.kw; ++kx, ++qw) {
-                    const uint32_t sw = qw % (uint32_t)p.w_stages;
-                    mbar_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u);
-                    if (kx == 0) mbar_wait(smem_u32(&bar_x_full[sx]), px);
-                    asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qw & 7u)) : "memory");
-                }
+                if (!p.w_resident)
+                    for (int kx = 0; kx < p.kw; ++kx, ++qw)
+                        timed_wait(smem_u32(&bar_w_full[qw % (uint32_t)p.w_stages]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                timed_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
+                asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qx & 7u)) : "memory");
             }
         }
+        if (timing && lane == 0) {
+            atomicAdd(p.timing + kTMmaWaitAcc, (unsigned long long)tw_acc);
+            atomicAdd(p.timing + kTMmaWaitW, (unsigned long long)tw_w);
+            atomicAdd(p.timing + kTGateWaitX, (unsigned long long)tw_x);
+        }
       } else if (warp == kLoadWarp) {
-        // ===================== weight loader: tile (ky, kx, cb) per pass, in the order the MMA warp consumes them =====================
+        // ===================== weight loader =====================
         if (lane == 0) {
-            uint32_t qw = 0;
+            long long tw_w = 0;
+            const long long t_begin = timing ? clock64() : 0;
             const size_t tile_floats = (size_t)p.w_tile_bytes / 4;
-            for (int ul = 0; ul < n_units_cta; ++ul) {
-                for (int st = 0; st < n_st; ++st) {
-                    const int ky = st / p.ncb, cb = st - ky * p.ncb;
-                    for (int kx = 0; kx < p.kw; ++kx, ++qw) {
-                        const int sw = (int)(qw % (uint32_t)p.w_stages);
-                        const uint32_t use = qw / (uint32_t)p.w_stages;
-                        if (use > 0) mbar_wait(smem_u32(&bar_w_empty[sw]), (use - 1) & 1u);
-                        const float *src = p.wimg + (size_t)((ky * p.kw + kx) * p.ncb + cb) * tile_floats;
-                        if (p.debug & 16) { mbar_arrive(smem_u32(&bar_w_full[sw])); continue; }
-                        mbar_expect_tx(smem_u32(&bar_w_full[sw]), p.w_tile_bytes);
-                        bulk_g2s(smem_u32(smem_w + (size_t)sw * p.w_tile_bytes), src, p.w_tile_bytes, smem_u32(&bar_w_full[sw]));
+            if (p.w_resident) {
+                // every tile once, in image order (slot = (ky*kw + kx)*ncb + cb), one barrier for all of them
+                const uint32_t n_tiles = (uint32_t)(p.kh * p.kw * p.ncb);
+                if (!(p.debug & 16)) {
+                    mbar_expect_tx(smem_u32(&bar_w_full[0]), n_tiles * p.w_tile_bytes);
+                    for (uint32_t t = 0; t < n_tiles; ++t)
+                        bulk_g2s(smem_u32(smem_w + (size_t)t * p.w_tile_bytes), p.wimg + (size_t)t * tile_floats, p.w_tile_bytes, smem_u32(&bar_w_full[0]));
+                } else {
+                    mbar_arrive(smem_u32(&bar_w_full[0]));
+                }
+            } else {
+                uint32_t qw = 0;
+                for (int ul = 0; ul < n_units_cta; ++ul) {
+                    for (int st = 0; st < n_st; ++st) {
+                        const int ky = st / p.ncb, cb = st - ky * p.ncb;
+                        for (int kx = 0; kx < p.kw; ++kx, ++qw) {
+                            const int sw = (int)(qw % (uint32_t)p.w_stages);
+                            const uint32_t use = qw / (uint32_t)p.w_stages;
+                            if (use > 0) timed_wait(smem_u32(&bar_w_empty[sw]), (use - 1) & 1u, timing, tw_w);
+                            const float *src = p.wimg + (size_t)((ky * p.kw + kx) * p.ncb + cb) * tile_floats;
+                            if (p.debug & 16) { mbar_arrive(smem_u32(&bar_w_full[sw])); continue; }
+                            mbar_expect_tx(smem_u32(&bar_w_full[sw]), p.w_tile_bytes);
+                            bulk_g2s(smem_u32(smem_w + (size_t)sw * p.w_tile_bytes), src, p.w_tile_bytes, smem_u32(&bar_w_full[sw]));
+                        }
                     }
                 }
+            }
+            if (timing) {
+                atomicAdd(p.timing + kTLoadTotal, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(p.timing + kTLoadWaitW, (unsigned long long)tw_w);
             }
         }
       } else if (warp == kSiteWarp) {
@@ -305,32 +430,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
         }
       }
     } else {
-        // ===================== producers: all 12 warps fill one stage together =====================
-        // Pair i of thread pt is (tile row, chunk) number pt + 384 i of the stage's P x CB/4 pairs: consecutive threads take
-        // consecutive 16-byte chunks of consecutive pixels, i.e. consecutive addresses of the channel-last source row.
+        // ===================== producers: G groups of warps, group g fills the stages q = g, g + G, ... =====================
+        // Pair i of thread pt is (tile row, chunk) number pt + T i of the stage's P x CB/4 pairs (T = threads of the group):
+        // consecutive threads take consecutive 16-byte chunks of consecutive pixels, i.e. consecutive addresses of the
+        // channel-last source row.  A stage is one dependent chain - global loads, conversion, shared-memory stores, the proxy
+        // fence (whose MEMBAR waits for every access the thread has in flight) and the arrive - of about one memory latency; the
+        // groups run their chains side by side, which is what hides that latency (a single group of 12 warps with the next
+        // stage's loads in flight across the fence was producer-bound: 2.3 k cycles per stage, profiles/r2_summary.md).
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
-        const int pt = tid - kProdWarp0 * 32;
-        const int cshift = p.CB == 32 ? 3 : 2;                // chunks per tile row = CB / 4
+        const int G = p.prod_groups;
+        const int gthreads = (12 / G) * 32;
+        const int pidx = tid - kProdWarp0 * 32;
+        const int g = pidx / gthreads, pt = pidx - g * gthreads;
+        constexpr int cshift = kCB == 32 ? 3 : 2;             // chunks per tile row = CB / 4
         const int n_pairs = p.P << cshift;
         const uint32_t x_base = smem_u32(smem_x);
-        struct Pos { int ul, st; uint32_t q; };
         const uint32_t q_end = (uint32_t)n_units_cta * (uint32_t)n_st;
+        long long tw_si = 0, tw_x = 0;
+        const long long t_begin = timing ? clock64() : 0;
         int ready_ul = -1;
         UnitInfo cur_u;
         cur_u.s = cur_u.y0 = cur_u.x0 = cur_u.valid = 0;
-        auto load = [&](const Pos &c, float4 (&f)[kRtMaxPairs], float4 (&a)[kRtMaxPairs]) {
-            if (c.ul > ready_ul) {
-                const int buf = c.ul % kRtRing;
-                mbar_wait(smem_u32(&bar_u_full[buf]), (uint32_t)(c.ul / kRtRing) & 1u);
+        int ul = 0, st = g;
+        while (st >= n_st) { st -= n_st; ++ul; }
+        for (uint32_t q = (uint32_t)g; q < q_end; q += (uint32_t)G) {
+            if (ul > ready_ul) {
+                const int buf = ul % kRtRing;
+                timed_wait(smem_u32(&bar_u_full[buf]), (uint32_t)(ul / kRtRing) & 1u, timing && pt == 0, tw_si);
                 cur_u = s_unit[buf];
-                mbar_arrive(smem_u32(&bar_u_free[buf]));
-                ready_ul = c.ul;
+                ready_ul = ul;
             }
-            const int ky = c.st / p.ncb, cb = c.st - ky * p.ncb;
-            const char *base = reinterpret_cast<const char *>(p.srcF + (long long)cur_u.s * p.src_stride + cb * p.CB);
+            const int ky = st / p.ncb, cb = st - ky * p.ncb;
+            const char *base = reinterpret_cast<const char *>(p.srcF + (long long)cur_u.s * p.src_stride + cb * kCB);
+            float4 f[kRtMaxPairs], a[kRtMaxPairs];
 #pragma unroll
             for (int i = 0; i < kRtMaxPairs; ++i) {
-                const int pr = pt + kRtProdThreads * i;
+                const int pr = pt + gthreads * i;
                 const int t = pr >> cshift, ch = pr & ((1 << cshift) - 1);
                 const int rr = t >> p.sw_shift, j = t & (SW - 1);
                 const int iy = cur_u.y0 + rr + ky - p.pad_t, ix = cur_u.x0 + j - p.pad_l;
@@ -339,15 +474,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
                 f[i] = __ldg(reinterpret_cast<const float4 *>(pf));
                 a[i] = __ldg(reinterpret_cast<const float4 *>(pf + p.a_minus_f));
             }
-        };
-        auto store = [&](const Pos &c, const float4 (&f)[kRtMaxPairs], const float4 (&a)[kRtMaxPairs]) {
-            const uint32_t sx = c.q % (uint32_t)p.x_stages, use = c.q / (uint32_t)p.x_stages;
-            if (use > 0) mbar_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u);
+            const uint32_t sx = q % (uint32_t)p.x_stages, use = q / (uint32_t)p.x_stages;
+            if (use > 0) timed_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing && pt == 0, tw_x);
             const uint32_t xs = x_base + sx * x_stage_bytes;
             if (!(p.debug & 2)) {
 #pragma unroll
                 for (int i = 0; i < kRtMaxPairs; ++i) {
-                    const int pr = pt + kRtProdThreads * i;
+                    const int pr = pt + gthreads * i;
                     if (pr >= n_pairs) break;
                     const int t = pr >> cshift, ch = pr & ((1 << cshift) - 1);
                     const float2 s01 = make_float2(slope_of(f[i].x, p.alpha), slope_of(f[i].y, p.alpha));
@@ -355,7 +488,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
                     const float2 v01 = __fmul2_rn(make_float2(f[i].x, f[i].y), s01), v23 = __fmul2_rn(make_float2(f[i].z, f[i].w), s23);
                     const float2 w01 = __fmul2_rn(make_float2(a[i].x, a[i].y), s01), w23 = __fmul2_rn(make_float2(a[i].z, a[i].w), s23);
                     float4 h, l;
-                    const uint32_t o = xs + rt_off(t, ch, p.row_bytes);
+                    const uint32_t o = xs + rt_off(t, ch, kCB * 4);
                     split2(v01.x, v01.y, h.x, h.y, l.x, l.y);
                     split2(v23.x, v23.y, h.z, h.w, l.z, l.w);
                     sts128(o, h);
@@ -369,26 +502,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_x_full[sx]));
-        };
-        auto advance = [&](Pos &c) {
-            ++c.q;
-            if (++c.st == n_st) { c.st = 0; ++c.ul; }
-        };
-        Pos cur;
-        cur.ul = 0; cur.st = 0; cur.q = 0;
-        float4 fa[kRtMaxPairs], aa[kRtMaxPairs], fb[kRtMaxPairs], ab4[kRtMaxPairs];
-        load(cur, fa, aa);
-        while (true) {
-            Pos nxt = cur;
-            advance(nxt);
-            if (nxt.q < q_end) load(nxt, fb, ab4);
-            store(cur, fa, aa);
-            if (nxt.q >= q_end) break;
-            cur = nxt;
-            advance(cur);
-            if (cur.q < q_end) load(cur, fa, aa);
-            store(nxt, fb, ab4);
-            if (cur.q >= q_end) break;
+            st += G;
+            while (st >= n_st) { st -= n_st; ++ul; }
+        }
+        if (timing && pidx == 0) {
+            atomicAdd(p.timing + kTProdTotal, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.timing + kTProdWaitSite, (unsigned long long)tw_si);
+            atomicAdd(p.timing + kTProdWaitStage, (unsigned long long)tw_x);
         }
     }
 

@@ -341,7 +341,7 @@ class EventNetCuda:
 
     TC_TIMING_SLOTS = ("mma_total", "mma_wait_acc", "mma_wait_sites", "mma_wait_weights", "prod_total", "prod_wait_siteinfo",
                        "prod_wait_stage", "epi_total", "epi_wait_acc", "epi_wait_siteinfo", "load_total", "load_wait", "ctas", "units",
-                       "gate_wait_sites")
+                       "gate_wait_sites", "mma_section")
 
     def tc_timing(self, enable=True):
         N.check(self._lib.aec_net_tc_timing(self._h, 1 if enable else 0, 0, None))

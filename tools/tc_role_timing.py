@@ -36,8 +36,9 @@ for nm, d in net.read_tc_timing().items():
     c = max(1, d["ctas"])
     f = lambda k, tot: 100.0 * d[k] / max(1, d[tot])
     print("%-6s ctas %4d units/cta %.1f | mma %7.0f kcyc/cta: gate-blocked %4.1f%% (gate waits: acc %4.1f%% sites %4.1f%% weights %4.1f%%) | prod %7.0f: wait info %4.1f%% stage %4.1f%% | "
-          "epi %7.0f: wait acc %4.1f%% info %4.1f%% | load wait %4.1f%%" % (
+          "epi %7.0f: wait acc %4.1f%% info %4.1f%% | load wait %4.1f%% | mma section (slot 15) %4.1f%%" % (
               nm, d["ctas"], d["units"] / c, d["mma_total"] / c / 1e3, f("mma_wait_sites", "mma_total"), f("mma_wait_acc", "mma_total"), f("gate_wait_sites", "mma_total"),
               f("mma_wait_weights", "mma_total"), d["prod_total"] / c / 1e3, f("prod_wait_siteinfo", "prod_total"), f("prod_wait_stage", "prod_total"),
-              d["epi_total"] / c / 1e3, f("epi_wait_acc", "epi_total"), f("epi_wait_siteinfo", "epi_total"), f("load_wait", "load_total")))
+              d["epi_total"] / c / 1e3, f("epi_wait_acc", "epi_total"), f("epi_wait_siteinfo", "epi_total"), f("load_wait", "load_total"),
+              f("mma_section", "mma_total")))
 net.close()
