@@ -329,7 +329,7 @@ static void build_rt_image(HostLayer &l, const float *kernel_hwio)
     const int cpad = l.Mrows;                                          // channels rounded up to 16 (sites-as-M)
     l.rt_xtile = ((size_t)l.rt_P * row_bytes + 1023) / 1024 * 1024;
     l.rt_wtile = (size_t)2 * cpad * row_bytes;
-    const size_t budget = 217 * 1024;                // 227 KB per CTA minus the alignment slack and the kernel's static shared memory
+    const size_t budget = 208 * 1024;                // 227 KB per CTA minus the alignment slack and the kernel's ~18 KB of static shared memory
     const size_t all_w = (size_t)l.kh * l.kw * l.rt_ncb * l.rt_wtile;
     l.rt_wres = all_w <= 48 * 1024 && all_w + 2 * 4 * l.rt_xtile <= budget;   // resident weights (aec_rt.cuh): no streaming latency
     if (l.rt_wres) {
@@ -601,11 +601,12 @@ static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
     p.debug = n->tc_debug;
     p.prod_groups = l.rt_groups;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
-    const bool staged = l.C > 32;          // epilogue stores through the per-warp transpose buffer (aec_rt.cuh)
-    if (l.rt_CB == 32 && staged) rt::k_conv_rows<32, true><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
-    else if (l.rt_CB == 32) rt::k_conv_rows<32, false><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
-    else if (staged) rt::k_conv_rows<16, true><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
-    else rt::k_conv_rows<16, false><<<n->num_sms, tc::kTcThreads, l.rt_smem, st>>>(p);
+    static const int staged_min = getenv("AEC_RT_STAGED_MIN_C") ? atoi(getenv("AEC_RT_STAGED_MIN_C")) : 33;
+    const bool staged = l.C >= staged_min;   // epilogue stores through the per-warp transpose buffer (aec_rt.cuh)
+    if (l.rt_CB == 32 && staged) rt::k_conv_rows<32, true><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
+    else if (l.rt_CB == 32) rt::k_conv_rows<32, false><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
+    else if (staged) rt::k_conv_rows<16, true><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
+    else rt::k_conv_rows<16, false><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_rows");
     return rc ? rc : prof_mark(n, st);
 }
@@ -942,9 +943,9 @@ extern "C" int aec_net_finalize(aec_net *n)
             if (rt_max + fa.sharedSizeBytes > 227 * 1024)
                 return fail(AEC_EINVAL, "row-tile conv kernel needs %zu + %zu bytes of shared memory", rt_max, (size_t)fa.sharedSizeBytes);
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_max));
-            const int pool = fa.numRegs * tc::kTcThreads;
-            const int want = 128 * tc::kRegsEpi + 128 * tc::kRegsCtl + 384 * tc::kRegsProd;
-            if (want > pool || fa.numRegs > tc::kRegsProd || fa.numRegs < tc::kRegsEpi)
+            const int pool = fa.numRegs * rt::kRtThreads;
+            const int want = rt::kRtEpiWarps * 32 * rt::kRtRegsEpi + 128 * rt::kRtRegsCtl + 384 * rt::kRtRegsProd;
+            if (want > pool || fa.numRegs > rt::kRtRegsProd || fa.numRegs < rt::kRtRegsEpi)
                 return fail(AEC_EINVAL, "row-tile conv kernel was built with %d registers/thread; the role split needs %d of %d", fa.numRegs, want, pool);
         }
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_conv_eval<16, 2, 4, 16>, kThreads, 0));

@@ -34,6 +34,15 @@ constexpr int kRtMaxXStages = 3;
 constexpr int kRtMaxWStages = 6;
 constexpr int kRtRing = 4;            // unit-info buffers
 constexpr int kRtProdThreads = kGroups * kGroupThreads;   // 384
+// Warp roles of the row-tile CTA (768 threads): EIGHT epilogue warps - the four TMEM lane quarters are readable by warps
+// with the matching (warp % 4) only, and four warps were the slowest role of the first version (profiles/r2_summary.md), so
+// every quarter has two, each taking every other 16-channel chunk - then the MMA issuer, weight loader, unit decoder,
+// gatekeeper, and 12 producer warps.  Registers after the role split: 256 x 72 + 128 x 48 + 384 x 96 = 768 x 80.
+constexpr int kRtThreads = 768;
+constexpr int kRtEpiWarps = 8;
+constexpr int kRtMmaWarp = 8, kRtLoadWarp = 9, kRtUnitWarp = 10, kRtGateWarp = 11;
+constexpr int kRtProdWarp0 = 12;
+constexpr int kRtRegsEpi = 72, kRtRegsCtl = 48, kRtRegsProd = 96;
 constexpr int kRtMaxPairs = 6;        // (tile row, 16-byte chunk) pairs per producer thread and stage
 
 struct RtParams {
@@ -90,7 +99,7 @@ __device__ __forceinline__ uint32_t rt_off(int t, int c, int row_bytes)
 // kCB = channels per block (16: 64-byte tile rows, SWIZZLE_64B; 32: 128-byte rows, SWIZZLE_128B) is a template parameter so
 // that the MMA issue loop and the producers' index arithmetic are compile-time shapes; kStaged selects the epilogue's store path.
 template <int kCB, bool kStaged>
-__global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_constant__ RtParams p)
+__global__ void __launch_bounds__(kRtThreads, 1) k_conv_rows(const __grid_constant__ RtParams p)
 {
     extern __shared__ unsigned char rt_smem_raw[];
     // Weights: a layer whose kh*kw*ncb tiles fit (conv2: 36 KB) keeps them RESIDENT - loaded once per CTA, bar_w_full[0] - because a
@@ -101,8 +110,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_u_full[kRtRing], bar_u_free[kRtRing];
     __shared__ uint32_t s_tmem;
     __shared__ UnitInfo s_unit[kRtRing];
-    __shared__ __align__(16) float s_etile[kEpiWarps][32 * 16];       // epilogue: one 32 sites x 16 channels chunk per warp (transpose buffer)
-    __shared__ long long s_edst[kEpiWarps][32];                       // epilogue: destination byte offset of the warp's sites (-1: no store)
+    __shared__ __align__(16) float s_etile[kRtEpiWarps][32 * 16];       // epilogue: one 32 sites x 16 channels chunk per warp (transpose buffer)
+    __shared__ long long s_edst[kRtEpiWarps][32];                       // epilogue: destination byte offset of the warp's sites (-1: no store)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total_units = __shfl_sync(0xffffffffu, *p.counter, 0);
@@ -127,11 +136,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bar_acc_full[i]), 1);
-            mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps * 32);
+            mbar_init(smem_u32(&bar_acc_empty[i]), kRtEpiWarps * 32);
         }
         for (int i = 0; i < kRtRing; ++i) {
             mbar_init(smem_u32(&bar_u_full[i]), 1);
-            mbar_init(smem_u32(&bar_u_free[i]), kEpiWarps * 32);          // the epilogue is the last role to finish a unit: its release is enough
+            mbar_init(smem_u32(&bar_u_free[i]), kRtEpiWarps * 32);          // the epilogue is the last role to finish a unit: its release is enough
         }
         fence_barrier_init();
     }
@@ -148,12 +157,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
     const int SW = 1 << p.sw_shift;
     const bool timing = p.timing != nullptr;
 
-    if (warp < kEpiWarps) {
-        // ===================== epilogue: one thread = one site of the tile =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-        const int m = warp * 32 + lane;
+    if (warp < kRtEpiWarps) {
+        // ===================== epilogue: one thread = one site of the tile, two warps per TMEM lane quarter =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRtRegsEpi));
+        const int quarter = warp & 3, half = warp >> 2;      // this warp takes the 16-channel chunks ci = half, half + 2, ...
+        const int m = quarter * 32 + lane;
         const int rr = m >> p.sw_shift, x = m & (SW - 1);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int cpad = p.Cpad;
         const int nch = (p.C + 15) >> 4;
         const int total = 2 * nch;
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
             mbar_arrive(smem_u32(&bar_u_free[buf]));          // every stage of this unit is complete: no role needs its slot any more
             const bool site_ok = dst >= 0 && !(p.debug & 8);
             const uint32_t tbase = lane_addr + (uint32_t)(ab * 4 * cpad);
-            uint32_t ra[16], rb[16], rc[16], rd[16];
+            uint32_t ra[16], rb[16];
             auto issue = [&](int ci, uint32_t(&hi)[16], uint32_t(&lo)[16]) {
                 const int map = ci >= nch ? 1 : 0, c0 = (ci - map * nch) << 4;
                 const uint32_t ta = tbase + (uint32_t)(map * 2 * cpad + c0);
@@ -259,15 +269,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
                 }
                 __syncwarp();
             };
-            issue(0, ra, rb);
 #pragma unroll 1
-            for (int ci = 0; ci < total; ci += 2) {
+            for (int ci = half; ci < total; ci += 2) {         // the other warp of the quarter takes the chunks in between
+                issue(ci, ra, rb);
                 tmem_ld_wait();
-                issue(ci + 1, rc, rd);
                 emit(ci, ra, rb);
-                tmem_ld_wait();
-                if (ci + 2 < total) issue(ci + 2, ra, rb);
-                emit(ci + 1, rc, rd);
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bar_acc_empty[ab]));
@@ -281,9 +287,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
             atomicAdd(p.timing + kTCtas, 1ULL);
             atomicAdd(p.timing + kTUnits, (unsigned long long)n_units_cta);
         }
-    } else if (warp < kProdWarp0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
-      if (warp == kMmaWarp) {
+    } else if (warp < kRtProdWarp0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRtRegsCtl));
+      if (warp == kRtMmaWarp) {
         // ===================== MMA issuer (no mbarrier waits here: see aec_tc.cuh) =====================
         // The issue loop is kept as lean as the compiler allows: one thread issues an instruction every few cycles, so a
         // descriptor rebuilt from an address per MMA (shift, mask, or: ~6 uniform-datapath instructions) makes the ISSUE
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
             atomicAdd(p.timing + kTMmaTotal, (unsigned long long)(clock64() - t_begin));
             atomicAdd(p.timing + kTMmaWaitX, (unsigned long long)tw_gate);
         }
-      } else if (warp == kGateWarp) {
+      } else if (warp == kRtGateWarp) {
         // ===================== gatekeeper: every wait of the MMA warp =====================
         uint32_t qx = 0, qw = 0;
         long long tw_acc = 0, tw_x = 0, tw_w = 0;
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
             atomicAdd(p.timing + kTMmaWaitW, (unsigned long long)tw_w);
             atomicAdd(p.timing + kTGateWaitX, (unsigned long long)tw_x);
         }
-      } else if (warp == kLoadWarp) {
+      } else if (warp == kRtLoadWarp) {
         // ===================== weight loader =====================
         if (lane == 0) {
             long long tw_w = 0;
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
                 atomicAdd(p.timing + kTLoadWaitW, (unsigned long long)tw_w);
             }
         }
-      } else if (warp == kSiteWarp) {
+      } else if (warp == kRtUnitWarp) {
         // ===================== unit decoder: work-list entry -> (stream, first row, first column) =====================
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
@@ -437,10 +443,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_rows(const __grid_consta
         // fence (whose MEMBAR waits for every access the thread has in flight) and the arrive - of about one memory latency; the
         // groups run their chains side by side, which is what hides that latency (a single group of 12 warps with the next
         // stage's loads in flight across the fence was producer-bound: 2.3 k cycles per stage, profiles/r2_summary.md).
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRtRegsProd));
         const int G = p.prod_groups;
         const int gthreads = (12 / G) * 32;
-        const int pidx = tid - kProdWarp0 * 32;
+        const int pidx = tid - kRtProdWarp0 * 32;
         const int g = pidx / gthreads, pt = pidx - g * gthreads;
         constexpr int cshift = kCB == 32 ? 3 : 2;             // chunks per tile row = CB / 4
         const int n_pairs = p.P << cshift;

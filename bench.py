@@ -552,23 +552,34 @@ def native_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # dominant kernel of the step: the gathered GEMM on the tensor cores (one launch per conv layer)
-    tc_ms = by_kernel.get("conv_eval_tc", 0.0)
-    fl = sum(layer_flops(net, i, sites_per_step[i]) for i in tc_layers)
+    # dominant kernel of the step: the tcgen05 conv re-evaluation - k_conv_rows (row tiles) or k_conv_eval_tc (gathered),
+    # whichever holds more of the step; the per-layer table carries every launch of both
     tf_pk, tf_src = tf32_peak(peaks, clocks.get("sm_mhz"))
-    tc_tflops = fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    n_tc = max(1, len(tc_layers))
     table = layer_table(net, prof, sites_per_step, S, tf_pk, peak, units_per_step)
-    issued = sum(table[net.names[i]].get("issued_TFLOPs", 0.0) * table[net.names[i]]["ms"] for i in tc_layers)
-    roofline = {"bound": "tensor", "kernel": "k_conv_rows / k_conv_eval_tc (tcgen05 conv re-evaluation, one launch per conv layer)", "achieved": tc_tflops, "peak": tf_pk, "unit": "TFLOP/s",
-                "frac": tc_tflops / tf_pk, "traffic": None, "peak_source": tf_src,
+    fam = {}
+    for i in tc_layers:
+        row = table[net.names[i]]
+        k = "k_conv_rows" if row.get("kernel", "").startswith("k_conv_rows") else "k_conv_eval_tc"
+        f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "issued": 0.0, "n": 0})
+        f["ms"] += row["ms"]
+        f["flops"] += layer_flops(net, i, sites_per_step[i])
+        f["issued"] += row.get("issued_TFLOPs", 0.0) * row["ms"]
+        f["n"] += 1
+    dom = max(fam, key=lambda k: fam[k]["ms"]) if fam else "k_conv_eval_tc"
+    fd = fam.get(dom, {"ms": 0.0, "flops": 0.0, "issued": 0.0, "n": 1})
+    tc_ms = by_kernel.get("conv_eval_tc", 0.0)
+    dom_tflops = fd["flops"] / (fd["ms"] * 1e-3) / 1e12 if fd["ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": dom_tflops, "peak": tf_pk, "unit": "TFLOP/s",
+                "frac": dom_tflops / tf_pk, "traffic": None, "peak_source": tf_src,
                 "precision": "3xTF32 (two or three tcgen05.mma.kind::tf32 per product for fp32-grade results): `achieved` counts "
                              "USEFUL FLOPs (2 x sites x {value, rate} x K x Cout); `issued` what the tensor pipe was asked to do, "
-                             "padding rows and split products included",
-                "issued_TFLOPs": issued / tc_ms if tc_ms > 0 else 0.0,
-                "issued_frac_of_peak": (issued / tc_ms / tf_pk) if tc_ms > 0 else 0.0,
-                "algorithmic_flops_per_launch": fl / n_tc, "launches_per_step": len(tc_layers), "kernel_ms": tc_ms / n_tc,
-                "kernel_share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
+                             "padding rows, gap sites of a row tile and split products included",
+                "issued_TFLOPs": fd["issued"] / fd["ms"] if fd["ms"] > 0 else 0.0,
+                "issued_frac_of_peak": (fd["issued"] / fd["ms"] / tf_pk) if fd["ms"] > 0 else 0.0,
+                "algorithmic_flops_per_launch": fd["flops"] / max(1, fd["n"]), "launches_per_step": fd["n"], "kernel_ms": fd["ms"] / max(1, fd["n"]),
+                "kernel_share_of_step": fd["ms"] / step_ms_prof if step_ms_prof else None,
+                "all_tcgen05_conv_kernels": {k: {"ms": round(v["ms"], 4), "launches": v["n"], "useful_TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else 0.0,
+                                                 "issued_TFLOPs": round(v["issued"] / v["ms"], 2) if v["ms"] > 0 else 0.0} for k, v in fam.items()},
                 "ms_by_kernel": {k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
                 "ms_by_launch": {k: round(v, 4) for k, v in prof.items()},
                 "layers": table,
@@ -580,7 +591,7 @@ def native_arm(args):
     except Exception:
         tj, same = None, False
     if same:
-        roofline["traffic"] = tj["dram_bytes_per_launch"].get("k_conv_eval_tc")
+        roofline["traffic"] = tj["dram_bytes_per_launch"].get(dom)
         roofline["traffic_source"] = tj["source"]
     # the dominant HBM-bound kernel: the leak sweep
     sweep_ms = prof.get("leak_sweep", 0.0)

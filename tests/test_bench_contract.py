@@ -48,6 +48,6 @@ def test_committed_traffic_file_matches_the_default_workload():
     workload; keep the two in step so the driver's bench line carries the number."""
     tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     assert tj["config"] == {"streams_per_gpu": 1024, "stream_kind": "edge", "batch_event_size": 200}
-    for k in ("k_conv_eval_tc", "k_leak_sweep", "k_pool_eval"):
+    for k in ("k_conv_rows", "k_conv_eval_tc", "k_leak_sweep", "k_pool_eval"):
         assert tj["dram_bytes_per_launch"][k] > 0 and tj["launches_per_step"][k] > 0
     assert "ncu --set full" in tj["source"]

@@ -23,7 +23,7 @@ def main(raw, out_md, out_json, note):
         lines.append("| %s | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f | %d | %d |" % (
             name[:36], us, rd, wr, val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), val(r, tensor),
             val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"), val(r, "launch__registers_per_thread"), val(r, "launch__grid_size")))
-        key = name.split("(")[0].replace("void ", "").split("<")[0].replace("tc::", "")
+        key = name.split("(")[0].replace("void ", "").split("<")[0].replace("tc::", "").replace("rt::", "")
         n, b = agg.get(key, (0, 0.0))
         agg[key] = (n + 1, b + (rd + wr) * 1e9)
     open(out_md, "w").write("\n".join(lines) + "\n")
