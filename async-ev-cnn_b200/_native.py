@@ -19,7 +19,7 @@ SYMBOLS = [
     "aec_net_state_bytes_per_stream", "aec_net_device_bytes", "aec_net_reset", "aec_net_step_device",
     "aec_net_step_host", "aec_net_head_device", "aec_net_head_elems_per_stream", "aec_net_read_head", "aec_net_begin_step",
     "aec_net_layer_compute", "aec_net_compute_head", "aec_net_read_size", "aec_net_read", "aec_net_read_step_info",
-    "aec_net_read_counters", "aec_net_launch_count", "aec_net_read_view", "aec_net_profile", "aec_net_read_profile",
+    "aec_net_read_counters", "aec_net_launch_count", "aec_net_read_view", "aec_net_profile", "aec_net_read_profile", "aec_net_profile_slot_name",
     "aec_net_count_nonzero_rate_groups", "aec_net_tc_timing", "aec_net_tc_geometry", "aec_net_read_unit_counters", "aec_net_sweep_stats", "aec_net_step_host_async", "aec_net_host_sync", "aec_net_decode_head", "aec_decode_ndata", "aec_split_batches", "aec_net_run_ndata",
 ]
 
@@ -116,6 +116,8 @@ def lib():
     L.aec_net_profile.argtypes = [vp, i]
     L.aec_net_read_profile.restype = i
     L.aec_net_read_profile.argtypes = [vp, vp, i, ctypes.POINTER(ull)]
+    L.aec_net_profile_slot_name.restype = i
+    L.aec_net_profile_slot_name.argtypes = [vp, i, ctypes.c_char_p, i]
     L.aec_net_count_nonzero_rate_groups.restype = i
     L.aec_net_count_nonzero_rate_groups.argtypes = [vp, ctypes.POINTER(ull), ctypes.POINTER(ull)]
     L.aec_net_tc_timing.restype = i

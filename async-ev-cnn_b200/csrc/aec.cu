@@ -72,6 +72,9 @@ struct HostLayer {
     std::vector<float> h_rtimg;
     float *rtimg = nullptr;
     uint32_t *nset = nullptr;      // [S][H*Ww] exact work set of the step (written by the frontier kernel)
+    // pool layer behind the FIRST conv layer: its sticky windows are evaluated by the leak sweep (SweepPool, aec_kernels.cuh)
+    bool swp_fused = false;
+    uint32_t *swp_uns = nullptr;
     size_t tc_smem = 0;
     std::vector<float> h_wimg;
     float *wimg = nullptr;
@@ -134,12 +137,15 @@ struct aec_net {
     int num_sms = 148;
     int sweep_chunks = 0, sweep_nconv = 0, sweep_conv_chunks = 0;
     SweepParams sweep_all;
+    SweepWindowsParams sweep_win;        // the first conv layer's map when the leak sweep also evaluates the pool behind it
+    int sweep_win_chunks = 0;
     unsigned long long launches = 0, steps = 0;
     int conv_eval_blocks[4] = {0, 0, 0, 0};
     // per-launch timing (aec_net_profile): one CUDA event between consecutive launches of a step
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // events of the current step (n_slots + 1)
     std::vector<double> prof_ms;            // accumulated ms per slot
+    std::vector<std::string> prof_names;    // name of the launch each slot timed ("surface", "L3.eval", ...), recorded on the first profiled step
     int prof_slot = 0;
     unsigned long long prof_steps = 0;
     bool tc_timing_on = false;
@@ -469,9 +475,16 @@ static int launch_check(aec_net *n, const char *what)
 
 // Profiling: an event is recorded on the launching stream after every launch of a step, so the
 // elapsed time between consecutive events is that kernel's duration inside the real step.
-static int prof_mark(aec_net *n, cudaStream_t st)
+static int prof_mark(aec_net *n, cudaStream_t st, const char *done = nullptr, int layer = -1)
 {
     if (!n->profiling) return AEC_OK;
+    if (done && n->prof_slot >= 1 && (int)n->prof_names.size() < n->prof_slot) {     // name of the launch that ends at this mark
+        char nm[64];
+        if (layer >= 0) snprintf(nm, sizeof nm, "L%d.%s", layer, done);
+        else snprintf(nm, sizeof nm, "%s", done);
+        n->prof_names.resize(n->prof_slot - 1);
+        n->prof_names.push_back(nm);
+    }
     if (n->prof_slot >= (int)n->prof_events.size()) {
         cudaEvent_t ev;
         CU(cudaEventCreate(&ev));
@@ -516,7 +529,7 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
     if ((rc = prof_mark(n, st))) return rc;
     k_integrate<<<n->S, kThreads, smem, st>>>(p);
     if ((rc = launch_check(n, "k_integrate"))) return rc;
-    return prof_mark(n, st);
+    return prof_mark(n, st, "surface");
 }
 
 // Fills one leak-sweep table entry; returns the number of chunks (grid.x slots) the layer takes.
@@ -542,11 +555,18 @@ static int fill_sweep_layer(const HostLayer &l, SweepLayer &o, int chunk0, bool 
 static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
 {
     if (only_layer < 0) {
+        int rc = AEC_OK;
+        if (n->sweep_win_chunks > 0) {
+            dim3 gridw(n->sweep_win_chunks, n->S);
+            k_sweep_windows<<<gridw, kThreads, 0, st>>>(n->sweep_win);
+            if ((rc = launch_check(n, "k_sweep_windows"))) return rc;
+            if ((rc = prof_mark(n, st, "window_sweep"))) return rc;
+        }
         if (n->sweep_all.n_layers == 0) return AEC_OK;
         dim3 grid(n->sweep_chunks, n->S);
         k_leak_sweep<<<grid, kThreads, 0, st>>>(n->sweep_all);
-        int rc = launch_check(n, "k_leak_sweep");
-        return rc ? rc : prof_mark(n, st);
+        rc = launch_check(n, "k_leak_sweep");
+        return rc ? rc : prof_mark(n, st, "leak_sweep");
     }
     SweepParams p;
     memset(&p, 0, sizeof p);
@@ -577,7 +597,7 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     else if (l.tc_fast_decode) tc::k_conv_eval_tc<true, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else tc::k_conv_eval_tc<false, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "eval", li);
 }
 
 // Row-tile evaluation: only inside the fused step, whose frontier kernel wrote the unit list and the work-set bitmap.
@@ -608,7 +628,7 @@ static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
     else if (staged) rt::k_conv_rows<16, true><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
     else rt::k_conv_rows<16, false><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_rows");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "eval", li);
 }
 
 static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = false)
@@ -626,7 +646,7 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = 
         if (l.kh == 3 && l.kw == 3) k_conv_stencil<3, 3><<<n->num_sms * 8, kThreads, 0, st>>>(p);
         else k_conv_stencil<0, 0><<<n->num_sms * 8, kThreads, 0, st>>>(p);
         int rc = launch_check(n, "k_conv_stencil");
-        return rc ? rc : prof_mark(n, st);
+        return rc ? rc : prof_mark(n, st, "eval", li);
     }
     ConvEvalParams p;
     p.sites = l.sites; p.counter = n->counts + li; p.accum = n->accum + li;
@@ -641,7 +661,7 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = 
     default: k_conv_eval<128, 8, 8, 16><<<n->conv_eval_blocks[3], kThreads, 0, st>>>(p); break;
     }
     int rc = launch_check(n, "k_conv_eval");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "eval", li);
 }
 
 static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
@@ -657,7 +677,7 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     else if (l.C % 4 == 0) k_pool_eval<4, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
     else k_pool_eval<1, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
     int rc = launch_check(n, "k_pool_eval");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "eval", li);
 }
 
 static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
@@ -676,7 +696,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
         const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4;
         k_conv_frontier<<<n->S, kThreads, smem, st>>>(p);
         if ((rc = launch_check(n, "k_conv_frontier"))) return rc;
-        if ((rc = prof_mark(n, st))) return rc;
+        if ((rc = prof_mark(n, st, "frontier", li))) return rc;
         return run_conv_eval(n, li, st);
     }
     if (with_sweep && (rc = run_sweep(n, li, st))) return rc;     // the (Fp, Ap) copy leaks before it is refreshed
@@ -688,7 +708,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4;
     k_pool_frontier<<<n->S, kThreads, smem, st>>>(p);
     if ((rc = launch_check(n, "k_pool_frontier"))) return rc;
-    if ((rc = prof_mark(n, st))) return rc;
+    if ((rc = prof_mark(n, st, "frontier", li))) return rc;
     return run_pool_eval(n, li, st);
 }
 
@@ -706,7 +726,7 @@ static int run_frontier_skip(aec_net *n, cudaStream_t st)
     p.max_words = n->front_max_words; p.active = n->active;
     k_frontier_skip<<<n->S, kThreads, (size_t)3 * n->front_max_words * 4, st>>>(p);
     int rc = launch_check(n, "k_frontier_skip");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "skip.frontier");
 }
 
 static int run_frontier_all(aec_net *n, cudaStream_t st)
@@ -717,7 +737,7 @@ static int run_frontier_all(aec_net *n, cudaStream_t st)
     p.max_words = n->front_max_words; p.active = n->active;
     k_frontier_all<<<n->S, kThreads, (size_t)5 * n->front_max_words * 4, st>>>(p);
     int rc = launch_check(n, "k_frontier_all");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "all.frontier");
 }
 
 static HeadParams head_params(aec_net *n, float *out)
@@ -737,7 +757,7 @@ static int run_head(aec_net *n, cudaStream_t st)
     int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
     k_head<<<blocks, kThreads, 0, st>>>(p);
     int rc = launch_check(n, "k_head");
-    return rc ? rc : prof_mark(n, st);
+    return rc ? rc : prof_mark(n, st, "head");
 }
 
 static int broadcast(aec_net *n, void *dst, const void *src, long long bytes_per_stream, long long stride_bytes,
@@ -784,6 +804,15 @@ extern "C" int aec_net_finalize(aec_net *n)
     int rc;
     const size_t S = (size_t)n->S;
     size_t maxHW = 0;
+    { const char *e = getenv("AEC_SWEEP_SKIP"); n->sweep_skip = !(e && atoi(e) == 0); }
+    {
+        // a 2x2 pool directly behind the FIRST conv layer: the leak sweep evaluates its sticky windows (AEC_SWEEP_POOL=0: never)
+        const char *e = getenv("AEC_SWEEP_POOL");
+        if (n->sweep_skip && !(e && atoi(e) == 0) && n->L.size() > 2 && n->L[1].type == AEC_LAYER_CONV && n->L[2].type == AEC_LAYER_POOL) {
+            HostLayer &pl = n->L[2];
+            pl.swp_fused = pl.kh == 2 && pl.kw == 2 && pl.stride == 2 && pl.C % 4 == 0;
+        }
+    }
     if ((rc = dev_alloc(n, &n->surface, S * n->H * n->W, true))) return rc;
     if ((rc = dev_alloc(n, &n->delta, S, true))) return rc;
     if ((rc = dev_alloc(n, &n->prev_ts, S, true))) return rc;
@@ -823,6 +852,7 @@ extern "C" int aec_net_finalize(aec_net *n)
             if ((rc = dev_alloc_map(n, &l.Fp, S * l.fstride))) return rc;
             if ((rc = dev_alloc_map(n, &l.Ap, S * l.fstride))) return rc;
             if ((rc = dev_alloc(n, &l.initFp, (size_t)l.fstride, false))) return rc;
+            if (l.swp_fused && (rc = dev_alloc(n, &l.swp_uns, S * bm, true))) return rc;
         }
         if (l.type != AEC_LAYER_INTEGRATION) maxHW = std::max(maxHW, (size_t)l.H * l.W);
     }
@@ -859,6 +889,7 @@ extern "C" int aec_net_finalize(aec_net *n)
             f.kh = l.kh; f.kw = l.kw; f.pad_t = l.pad_t; f.pad_l = l.pad_l; f.stride = l.stride; f.code = l.code;
             f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.skip = l.skip; f.sites = l.sites; f.counter = n->counts + li;
             f.rt_rows = l.rt ? l.rt_R : 0; f.rt_seg = l.rt_SEG; f.rt_nxg = l.rt_nxg; f.nset = l.nset; f.counter2 = n->counts + 32 + li;
+            f.swp_uns = l.swp_fused ? l.swp_uns : nullptr; f.swp_skip = pv.skip;
             mw = std::max(mw, std::max(pv.H * pv.Ww, std::max(pv.H * l.Ww, l.H * l.Ww)));
         }
         n->front_max_words = mw;
@@ -870,16 +901,32 @@ extern "C" int aec_net_finalize(aec_net *n)
     }
 
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
-    { const char *e = getenv("AEC_SWEEP_SKIP"); n->sweep_skip = !(e && atoi(e) == 0); }
     { const char *e = getenv("AEC_TC_DEBUG"); n->tc_debug = e ? atoi(e) : 0; }
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
     int chunk0 = 0, nc = 0;
+    n->sweep_win_chunks = 0;
     for (int pass = 0; pass < 2; ++pass) {
-        for (auto &l : n->L)
-            if (l.type == (pass == 0 ? AEC_LAYER_CONV : AEC_LAYER_POOL)) {
-                chunk0 += fill_sweep_layer(l, n->sweep_all.L[nc], chunk0, false, n->sweep_skip);
-                ++nc;
+        for (size_t li = 1; li < n->L.size(); ++li) {
+            HostLayer &l = n->L[li];
+            if (l.type != (pass == 0 ? AEC_LAYER_CONV : AEC_LAYER_POOL)) continue;
+            if (pass == 0 && li + 1 < n->L.size() && n->L[li + 1].swp_fused && l.C % 4 == 0) {
+                // this map is swept window by window by k_sweep_windows, which evaluates the pool layer's sticky windows on the way
+                const HostLayer &pl = n->L[li + 1];
+                SweepWindowsParams &w = n->sweep_win;
+                memset(&w, 0, sizeof w);
+                fill_sweep_layer(l, w.L, 0, false, true);
+                SweepPool &q = w.Q;
+                q.idx = pl.idx; q.Fp = pl.Fp; q.Ap = pl.Ap; q.pstride = pl.fstride; q.flags = pl.flags; q.uns = pl.swp_uns;
+                q.accum = n->accum + (li + 1);
+                q.pW = pl.W; q.pWw = pl.Ww; q.pHWw = pl.H * pl.Ww; q.alpha = l.alpha;
+                q.wpc = std::max(1, std::min(kSweepMaxWords, kSweepUnitsPerChunk / (32 * 4 * w.L.c4)));   // a window = four sites
+                w.delta = n->delta; w.active = n->active;
+                n->sweep_win_chunks = (q.pHWw + q.wpc - 1) / q.wpc;
+                continue;
             }
+            chunk0 += fill_sweep_layer(l, n->sweep_all.L[nc], chunk0, false, n->sweep_skip);
+            ++nc;
+        }
         if (pass == 0) { n->sweep_nconv = nc; n->sweep_conv_chunks = chunk0; }
     }
     n->sweep_all.n_layers = nc;
@@ -1405,6 +1452,7 @@ extern "C" int aec_net_profile(aec_net *n, int enable)
     n->profiling = enable != 0;
     n->prof_slot = 0;
     n->prof_steps = 0;
+    n->prof_names.clear();
     std::fill(n->prof_ms.begin(), n->prof_ms.end(), 0.0);
     return AEC_OK;
 }
@@ -1417,14 +1465,24 @@ extern "C" int aec_net_read_profile(aec_net *n, double *ms_per_slot, int n_slots
     return (int)n->prof_ms.size();
 }
 
+extern "C" int aec_net_profile_slot_name(aec_net *n, int slot, char *buf, int cap)
+{
+    if (!n || !buf || cap < 1) return fail(AEC_EINVAL, "profile_slot_name: bad arguments");
+    buf[0] = 0;
+    if (slot < 0 || slot >= (int)n->prof_names.size()) return 0;
+    snprintf(buf, (size_t)cap, "%s", n->prof_names[slot].c_str());
+    return (int)strlen(buf);
+}
+
 extern "C" int aec_net_count_nonzero_rate_groups(aec_net *n, unsigned long long *nz_groups, unsigned long long *total_groups)
 {
     NEED_FINAL(n);
     CU(cudaDeviceSynchronize());
     CU(cudaMemset(n->accum + 31, 0, sizeof(unsigned long long)));
     unsigned long long total = 0;
-    for (int i = 0; i < n->sweep_nconv; ++i) total += (unsigned long long)n->sweep_all.L[i].n4 * n->S;
-    if (n->sweep_nconv) {
+    for (auto &l : n->L)
+        if (l.type == AEC_LAYER_CONV) total += (unsigned long long)(l.fstride / 4) * n->S;
+    if (total) {
         SweepParams conv_only;
         memset(&conv_only, 0, sizeof conv_only);
         int nc = 0, chunk0 = 0;

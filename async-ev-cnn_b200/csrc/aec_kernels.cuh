@@ -410,9 +410,31 @@ struct SweepLayer {
     int wpc;             // sparse path: bitmap words per chunk (<= kSweepMaxWords)
     int c4, c4_shift;    // C/4 and log2(C/4) (or -1 when C/4 is not a power of two)
 };
+// The first conv layer's map is swept window by window when a 2x2 pool follows it (k_leak_sweep, fused path): a window that the
+// pool layer re-evaluates in this step only because its recompute flag is set (maxpool.py:123-126) and none of whose four conv
+// sites is re-evaluated reads exactly the values the sweep has in registers - the leaked F and A of its sites - so its argmax
+// is taken here instead of being read back by k_pool_eval.  That holds for the FIRST conv layer only: its work set (dilation
+// of the surface's events) is final before the sweep; a deeper layer's may still grow by the sign flips the sweep finds.
+struct SweepPool {
+    uint8_t *idx;              // [S][pstride] pool argmax rows
+    float *Fp, *Ap;            // [S][pstride] copies at the argmax
+    long long pstride;
+    const uint32_t *flags;     // [S][pHWw] sticky recompute flags as the previous step left them (the frontier kernel updates them later)
+    uint32_t *uns;             // [S][pHWw] out: windows evaluated here that came out unstable (consumed and cleared by k_frontier_all)
+    unsigned long long *accum; // windows evaluated here, added to the pool layer's work counter
+    int pW, pWw, pHWw;         // pool map width, bitmap words per row, words per stream
+    int wpc;                   // window-bitmap words per chunk
+    float alpha;
+};
 struct SweepParams {
     SweepLayer L[kMaxSweep];
     int n_layers;
+    const double *delta;
+    const uint8_t *active;
+};
+struct SweepWindowsParams {      // k_sweep_windows: one conv map swept by pool windows
+    SweepLayer L;
+    SweepPool Q;
     const double *delta;
     const uint8_t *active;
 };
@@ -451,6 +473,160 @@ __device__ __forceinline__ unsigned leak4v(float4 *Fp, const float4 f, const flo
     *Fp = g;
     return ((f.x >= 0.f) != (g.x >= 0.f) ? 1u : 0u) | ((f.y >= 0.f) != (g.y >= 0.f) ? 2u : 0u) |
            ((f.z >= 0.f) != (g.z >= 0.f) ? 4u : 0u) | ((f.w >= 0.f) != (g.w >= 0.f) ? 8u : 0u);
+}
+
+struct PoolBest {
+    float f, r, a, rlow;
+    int row;
+};
+__device__ __forceinline__ void pool_first(PoolBest &b, float f, float a, float alpha)
+{
+    b.f = f; b.a = a; b.r = __fmul_rn(a, slope_of(f, alpha)); b.rlow = b.r; b.row = 0;
+}
+__device__ __forceinline__ void pool_next(PoolBest &b, int row, float f, float a, float alpha)
+{
+    const float r = __fmul_rn(a, slope_of(f, alpha));
+    if (f > b.f || (f == b.f && r < b.r)) { b.row = row; b.f = f; b.r = r; b.a = a; }   // cutils.pyx:166-170
+    if (r < b.rlow) b.rlow = r;                                                          // cutils.pyx:173-174
+}
+
+
+// Fused path of the leak sweep (see SweepPool): one chunk = `wpc` words of the POOL layer's window bitmap.
+//   need  = windows holding a site that must be leaked (live and not re-evaluated)  U  sticky windows evaluated here
+//   item  = (window, 4 channels): the four sites' (A, F) vectors are loaded together (only where needed), live sites are leaked
+//           exactly like the plain sweep (same arithmetic, sign flips into signchg), and a sticky window none of whose sites
+//           is re-evaluated gets its argmax / (Fp, Ap) copy / unstable bit from those registers (cutils.pyx:161-177).
+// Its own kernel (grid: chunks x S) so that the plain sweep keeps its 48 registers per thread.
+__global__ void __launch_bounds__(kThreads) k_sweep_windows(const __grid_constant__ SweepWindowsParams p)
+{
+    __shared__ int s_win[kSweepMaxWords * 32];
+    __shared__ int s_scan[9];
+    const int s = blockIdx.y;
+    if (!p.active[s]) return;
+    const double delta = p.delta[s];
+    const SweepLayer &L = p.L;
+    const SweepPool &Q = p.Q;
+    const int chunk_local = blockIdx.x;
+    const float4 *A4 = reinterpret_cast<const float4 *>(L.A + (long long)s * L.fstride);
+    float4 *F4 = reinterpret_cast<float4 *>(L.F + (long long)s * L.fstride);
+    uint32_t *sc = L.signchg ? L.signchg + (long long)s * L.HWw : nullptr;
+    __shared__ uint32_t s_cw[kSweepMaxWords][4];      // per window word: live bits of its conv words (row 0: lo, hi; row 1: lo, hi)
+    __shared__ uint32_t s_fz[kSweepMaxWords];         // per window word: windows evaluated here
+    __shared__ int s_cnt;
+    const int w0 = chunk_local * Q.wpc, w1 = min(Q.pHWw, w0 + Q.wpc);
+    const uint32_t *nz = L.nzr + (long long)s * L.HWw;
+    const uint32_t *sk = L.skip + (long long)s * L.HWw;
+    const uint32_t *fl = Q.flags + (long long)s * Q.pHWw;
+    if (threadIdx.x == 0) s_cnt = 0;
+    uint32_t need = 0u;
+    if ((int)threadIdx.x < w1 - w0) {
+        const int w = w0 + threadIdx.x;
+        const int py = w / Q.pWw, pw = w - py * Q.pWw;
+        uint32_t live[4], nset[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cw = 2 * pw + (k & 1);
+            live[k] = 0u;
+            if (cw < L.Ww) {
+                const int i = (2 * py + (k >> 1)) * L.Ww + cw;
+                const uint32_t sv = __ldg(sk + i);
+                live[k] = __ldg(nz + i) & ~sv;
+                nset[k & 1] |= sv;
+            }
+            s_cw[threadIdx.x][k] = live[k];
+        }
+        auto pooled = [](uint32_t lo, uint32_t hi) {
+            lo |= lo >> 1;
+            hi |= hi >> 1;
+            return compress_even_bits(lo) | (compress_even_bits(hi) << 16);
+        };
+        const uint32_t lastmask = (Q.pW & 31) && pw == Q.pWw - 1 ? ((1u << (Q.pW & 31)) - 1u) : 0xffffffffu;
+        const uint32_t fz = __ldg(fl + w) & ~pooled(nset[0], nset[1]) & lastmask;
+        s_fz[threadIdx.x] = fz;
+        need = (pooled(live[0] | live[2], live[1] | live[3]) | fz) & lastmask;
+    }
+    if (!__syncthreads_or(need != 0u)) return;
+    int total;
+    int off = block_excl_scan(__popc(need), s_scan, &total);
+    {
+        const int wl = threadIdx.x;                   // window word (local)
+        while (need) {
+            const int b = __ffs(need) - 1;
+            need &= need - 1;
+            s_win[off++] = (wl << 5) | b;
+        }
+    }
+    __syncthreads();
+    const int c4 = L.c4;
+    const int items = total * c4;
+    const int cW = L.W;
+    int fused_here = 0;
+    for (int u = threadIdx.x; u < items; u += kThreads) {
+        const int wi = L.c4_shift >= 0 ? (u >> L.c4_shift) : (u / c4);
+        const int cg = u - wi * c4;
+        const int code = s_win[wi], wl = code >> 5, b = code & 31;
+        const int w = w0 + wl;
+        const int py = w / Q.pWw, px = (w - py * Q.pWw) * 32 + b;
+        const bool fused = (s_fz[wl] >> b) & 1u;
+        float4 a[4], f[4];
+        bool live[4];
+        int idx4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                  // k = window row: (dy, dx) = (k >> 1, k & 1)
+            const int cbit = 2 * b + (k & 1);          // conv column within the window word's 64 columns
+            live[k] = (s_cw[wl][(k >> 1) * 2 + (cbit >> 5)] >> (cbit & 31)) & 1u;
+            idx4[k] = ((2 * py + (k >> 1)) * cW + 2 * px + (k & 1)) * c4 + cg;
+            a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            f[k] = a[k];
+            if (live[k] || fused) {
+                a[k] = A4[idx4[k]];
+                f[k] = F4[idx4[k]];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!live[k]) continue;
+            const float4 av = a[k];
+            if (av.x == 0.f && av.y == 0.f && av.z == 0.f && av.w == 0.f) continue;
+            const float4 old = f[k];
+            float4 g;
+            g.x = leak1(old.x, av.x, delta);
+            g.y = leak1(old.y, av.y, delta);
+            g.z = leak1(old.z, av.z, delta);
+            g.w = leak1(old.w, av.w, delta);
+            F4[idx4[k]] = g;
+            f[k] = g;
+            const bool flip = ((old.x >= 0.f) != (g.x >= 0.f)) || ((old.y >= 0.f) != (g.y >= 0.f)) || ((old.z >= 0.f) != (g.z >= 0.f)) ||
+                              ((old.w >= 0.f) != (g.w >= 0.f));
+            if (flip && sc) {
+                const int y = 2 * py + (k >> 1), x = 2 * px + (k & 1);
+                atomicOr(&sc[y * L.Ww + (x >> 5)], 1u << (x & 31));
+            }
+        }
+        if (fused) {
+            const float fr[4][4] = {{f[0].x, f[0].y, f[0].z, f[0].w}, {f[1].x, f[1].y, f[1].z, f[1].w}, {f[2].x, f[2].y, f[2].z, f[2].w}, {f[3].x, f[3].y, f[3].z, f[3].w}};
+            const float ar[4][4] = {{a[0].x, a[0].y, a[0].z, a[0].w}, {a[1].x, a[1].y, a[1].z, a[1].w}, {a[2].x, a[2].y, a[2].z, a[2].w}, {a[3].x, a[3].y, a[3].z, a[3].w}};
+            PoolBest best[4];
+            bool unstable = false;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                pool_first(best[v], fr[0][v], ar[0][v], Q.alpha);
+#pragma unroll
+                for (int row = 1; row < 4; ++row) pool_next(best[v], row, fr[row][v], ar[row][v], Q.alpha);
+                unstable |= best[v].r != best[v].rlow;
+            }
+            const long long o = (long long)s * Q.pstride + ((long long)py * Q.pW + px) * L.C + 4 * cg;
+            *reinterpret_cast<uchar4 *>(Q.idx + o) = make_uchar4((unsigned char)best[0].row, (unsigned char)best[1].row,
+                                                                  (unsigned char)best[2].row, (unsigned char)best[3].row);
+            *reinterpret_cast<float4 *>(Q.Fp + o) = make_float4(best[0].f, best[1].f, best[2].f, best[3].f);
+            *reinterpret_cast<float4 *>(Q.Ap + o) = make_float4(best[0].a, best[1].a, best[2].a, best[3].a);
+            if (unstable) atomicOr(&Q.uns[(long long)s * Q.pHWw + w], 1u << b);
+            if (cg == 0) ++fused_here;
+        }
+    }
+    if (fused_here) atomicAdd(&s_cnt, fused_here);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(Q.accum, (unsigned long long)s_cnt);
 }
 
 __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__ SweepParams p)
@@ -745,6 +921,8 @@ struct FrontLayer {
     SiteCode code;
     int rt_rows, rt_seg, rt_nxg;  // row-tile conv layer (aec_rt.cuh): rows per unit (0 = the layer takes a site list), sites per x segment, segments per row
     uint32_t *nset;               // row-tile layer: [S][H*Ww] copy of the exact work set (the evaluation stores only there)
+    uint32_t *swp_uns;            // pool layer whose sticky windows the leak sweep evaluates (SweepPool): their unstable bits, else null
+    const uint32_t *swp_skip;     // ... and the conv layer's skip bitmap (= its exact work set: first conv layer only)
     int *counter2;                // row-tile layer: number of work-set sites (statistics)
     uint32_t *front, *signchg, *flags, *nzr;
     uint32_t *skip;               // [S][H*Ww] written by k_frontier_skip: a subset of this step's work set, known before the leak sweep
@@ -855,20 +1033,38 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
                 if (w == L.Ww - 1) hit &= lastmask;
                 return hit;
             };
+            const uint32_t *pskip = L.swp_uns ? L.swp_skip + (long long)s * L.Hin * L.WwIn : nullptr;
+            uint32_t *uns = L.swp_uns ? L.swp_uns + (long long)s * nout : nullptr;
             for (int i = tid; i < nout; i += kThreads) {
                 const uint32_t hit = window_or(bufA, i);
-                const uint32_t f = fl[i] & ~hit;      // maxpool.py:118-120
+                const uint32_t before = fl[i];
+                uint32_t f = before & ~hit;           // maxpool.py:118-120
                 const uint32_t wset = hit | f;        // maxpool.py:123-126
+                uint32_t todo = wset;                 // windows k_pool_eval has to evaluate
+                if (uns) {
+                    // windows the leak sweep has evaluated already (sticky flag set, none of their conv sites re-evaluated): they
+                    // stay output events of the layer but leave the work list; a window among them that was hit after all (by a
+                    // sign flip the sweep found) had its flag cleared above and gets it back if it came out unstable
+                    const uint32_t done = before & ~window_or(pskip, i);
+                    const uint32_t u = uns[i];
+                    if (u) uns[i] = 0u;
+                    f |= done & hit & u;
+                    todo &= ~done;
+                }
                 fl[i] = f;
-                N[i] = wset;
+                N[i] = todo;
                 front[i] = wset;
                 uint32_t z = nz[i];
                 if (wset) { z = (z & ~wset) | (wset & window_or(bufB, i)); nz[i] = z; }
                 Z[i] = z;
+                Hd[i] = wset;                         // Hd is free in the pool branch: the layer's output events for the next layer
             }
             __syncthreads();
-            for (int i = tid; i < nout; i += kThreads) bufA[i] = N[i];
+            emit_sites(N, L.H, L.Ww, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.sites, L.counter, scratch);
             __syncthreads();
+            for (int i = tid; i < nout; i += kThreads) { bufA[i] = Hd[i]; bufB[i] = Z[i]; }
+            __syncthreads();
+            continue;
         }
         if (L.type == 1 && L.rt_rows > 0) {
             // row-tile conv layer: the evaluation needs the work set itself (it stores only there) and one entry per active unit
@@ -991,21 +1187,6 @@ struct PoolEvalParams {
     int kh, kw, stride;
     SiteCode code;
 };
-
-struct PoolBest {
-    float f, r, a, rlow;
-    int row;
-};
-__device__ __forceinline__ void pool_first(PoolBest &b, float f, float a, float alpha)
-{
-    b.f = f; b.a = a; b.r = __fmul_rn(a, slope_of(f, alpha)); b.rlow = b.r; b.row = 0;
-}
-__device__ __forceinline__ void pool_next(PoolBest &b, int row, float f, float a, float alpha)
-{
-    const float r = __fmul_rn(a, slope_of(f, alpha));
-    if (f > b.f || (f == b.f && r < b.r)) { b.row = row; b.f = f; b.r = r; b.a = a; }   // cutils.pyx:166-170
-    if (r < b.rlow) b.rlow = r;                                                          // cutils.pyx:173-174
-}
 
 // WIN2: the 2x2 / stride-2 window of every EFCN pool layer, with the eight 16-byte loads of an item issued before
 // the first compare (the generic loop has run-time bounds and makes four dependent round trips to memory).

@@ -285,10 +285,19 @@ class EventNetCuda:
 
 
     # -- measurement ---------------------------------------------------------------------------
-    def slot_names(self):
-        """Names of the launches of one step, in order (matches aec_net_read_profile slots)."""
-        skip = ["skip.frontier"] if os.environ.get("AEC_SWEEP_SKIP", "1") != "0" else []      # k_frontier_skip (before the sweep)
-        return ["surface"] + skip + ["leak_sweep", "all.frontier"] + [nm + ".eval" for nm in self.names[1:]] + ["head"]
+    def slot_names(self, n_slots=64):
+        """Names of the launches of the last profiled step, in order, as the library recorded them
+        (aec_net_profile_slot_name): "L<i>.eval" becomes "<layer name>.eval"."""
+        out = []
+        buf = ctypes.create_string_buffer(64)
+        for i in range(n_slots):
+            if N.check(self._lib.aec_net_profile_slot_name(self._h, i, buf, 64)) == 0:
+                break
+            nm = buf.value.decode()
+            if nm.startswith("L") and "." in nm and nm[1:nm.index(".")].isdigit():
+                nm = self.names[int(nm[1:nm.index(".")])] + nm[nm.index("."):]
+            out.append(nm)
+        return out
 
     def profile(self, enable=True):
         N.check(self._lib.aec_net_profile(self._h, 1 if enable else 0))

@@ -593,24 +593,32 @@ def native_arm(args):
     if same:
         roofline["traffic"] = tj["dram_bytes_per_launch"].get(dom)
         roofline["traffic_source"] = tj["source"]
-    # the dominant HBM-bound kernel: the leak sweep
-    sweep_ms = prof.get("leak_sweep", 0.0)
-    achieved = ab["leak_sweep"] / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
-    roofline_hbm = {"bound": "hbm", "kernel": "k_leak_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # the HBM-bound group of the step: leak sweep (plain + window form, which also evaluates the first pool layer's sticky
+    # windows) and the pool evaluations - their algorithmic bytes against their summed in-step durations
+    sweep_ms = prof.get("leak_sweep", 0.0) + prof.get("window_sweep", 0.0)
+    pool_ms = sum(v for k, v in prof.items() if k.endswith(".eval") and "pool" in k)
+    grp_ms = sweep_ms + pool_ms
+    grp_bytes = ab["leak_sweep"] + ab["pool"]
+    achieved = grp_bytes / (grp_ms * 1e-3) / 1e9 if grp_ms > 0 else 0.0
+    roofline_hbm = {"bound": "hbm", "kernel": "k_sweep_windows + k_leak_sweep + k_pool_eval (leak of the conv maps and pool re-evaluation)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ab["leak_sweep"], "kernel_ms": sweep_ms,
-                    "kernel_share_of_step": sweep_ms / step_ms_prof if step_ms_prof else None,
+                    "algorithmic_bytes_per_step": grp_bytes, "leak_bytes": ab["leak_sweep"], "pool_bytes": ab["pool"],
+                    "kernel_ms": grp_ms, "sweep_ms": sweep_ms, "pool_ms": pool_ms,
+                    "kernel_share_of_step": grp_ms / step_ms_prof if step_ms_prof else None,
                     "live_site_fraction": sw["live_conv_elems"] / max(1, sw["conv_elems"]),
                     "swept_fraction": sw.get("swept_conv_elems", sw["live_conv_elems"]) / max(1, sw["conv_elems"]),
                     "nonzero_rate_group_fraction": sw["nz_groups"] / max(1, sw["groups"]),
-                    "unaccounted": "the pool layers' (Fp, Ap) copies swept by the same launch (%.3g of %.3g elements x 12 B) are not in the algorithmic bytes" % (
+                    "unaccounted": "the pool layers' (Fp, Ap) copies swept by the same launches (%.3g of %.3g elements x 12 B) are not in the algorithmic bytes" % (
                         sw.get("swept_pool_elems", sw["live_pool_elems"]), sw["pool_elems"]),
                     "whole_step": {"algorithmic_bytes": ab["total"], "achieved_gbs": ab["total"] / (ms_total / K * 1e-3) / 1e9,
                                    "frac": ab["total"] / (ms_total / K * 1e-3) / 1e9 / peak,
                                    "note": "bytes the implemented algorithm needs (sparse leak sweep + measured frontier terms, SURVEY 8(d) "
                                            "with the leak term restricted to the sites that are swept)"}}
     if same:
-        roofline_hbm["traffic"] = tj["dram_bytes_per_launch"].get("k_leak_sweep")
+        d = tj["dram_bytes_per_launch"]
+        lp = tj["launches_per_step"]
+        roofline_hbm["traffic"] = sum(d.get(k, 0.0) * lp.get(k, 1) for k in ("k_leak_sweep", "k_sweep_windows", "k_pool_eval"))
 
     # ---- end to end through the multi-GPU product path (ShardedEventNet): pinned host events in; every rank's head is
     # copied by its own GPU straight into its rows of ONE shared page-locked host array, so after sync() rank 0 holds

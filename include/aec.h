@@ -217,6 +217,13 @@ int aec_net_read_counters(aec_net *net, unsigned long long *sites, int n_layers,
  */
 int aec_net_profile(aec_net *net, int enable);
 int aec_net_read_profile(aec_net *net, double *ms_per_slot, int n_slots, unsigned long long *steps);
+/*
+ * Name of the launch that profile slot `slot` timed, as recorded on the first profiled step: "surface",
+ * "skip.frontier", "window_sweep", "leak_sweep", "all.frontier", "L<layer index>.eval" / "L<layer index>.frontier", "head".
+ * Writes a NUL-terminated string into buf (capacity cap); returns its length, 0 for a slot that was never recorded.
+ */
+int aec_net_profile_slot_name(aec_net *net, int slot, char *buf, int cap);
+
 
 /*
  * Measurement helper: counts the 16-byte groups of the conv leak-rate maps that hold a non-zero
