@@ -1414,7 +1414,7 @@ extern "C" int aec_net_read_unit_counters(aec_net *n, unsigned long long *units,
     CU(cudaDeviceSynchronize());
     unsigned long long tmp[64];
     CU(cudaMemcpy(tmp, n->accum, sizeof tmp, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n_layers && i < 31; ++i) units[i] = (i < (int)n->L.size() && n->L[i].rt) ? tmp[32 + i] : 0ULL;
+    for (int i = 0; i < n_layers && i < 31; ++i) units[i] = (i < (int)n->L.size() && (n->L[i].rt || n->L[i].swp_fused)) ? tmp[32 + i] : 0ULL;
     return AEC_OK;
 }
 

@@ -626,7 +626,10 @@ __global__ void __launch_bounds__(kThreads) k_sweep_windows(const __grid_constan
     }
     if (fused_here) atomicAdd(&s_cnt, fused_here);
     __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) atomicAdd(Q.accum, (unsigned long long)s_cnt);
+    if (threadIdx.x == 0 && s_cnt) {
+        atomicAdd(Q.accum, (unsigned long long)s_cnt);
+        atomicAdd(Q.accum + 32, (unsigned long long)s_cnt);   // [32 + l]: the share of the pool layer's windows evaluated here
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__ SweepParams p)

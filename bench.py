@@ -312,6 +312,13 @@ def layer_table(net, prof, sites_per_step, streams, tf32_pk, hbm_pk, units_per_s
                     row["kernel"] = "k_conv_stencil / k_conv_eval (SIMT)"
             else:
                 row["kernel"] = "k_pool_eval"
+                in_sweep = float(units_per_step[i]) if units_per_step is not None else 0.0
+                if in_sweep > 0:
+                    # windows evaluated inside k_sweep_windows cost no time here: rate this launch on the windows it evaluated
+                    b = layer_bytes(net, i, n - in_sweep, streams)
+                    row.update({"windows_in_leak_sweep_per_stream": round(in_sweep / streams, 1), "alg_GB": round(b / 1e9, 4),
+                                "alg_GBps": round(b / (ms * 1e-3) / 1e9, 1), "hbm_frac": round(b / (ms * 1e-3) / 1e9 / hbm_pk, 4),
+                                "kernel": "k_pool_eval (the remaining windows; the rest in k_sweep_windows, see window_sweep in ms_by_launch)"})
         rows[nm] = row
     return rows
 

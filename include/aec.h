@@ -314,8 +314,9 @@ int aec_net_tc_geometry(const aec_net *net, int layer, long long *out8);
 
 /*
  * Measurement helper: work units evaluated per layer since the last counter reset, for the layers that run on the
- * row-tile kernel (aec_net_tc_geometry out8[7] == 1; a unit = 128 tile sites, work-set sites and gaps alike); 0 for
- * every other layer.  Reset together with aec_net_read_counters(reset = 1).
+ * row-tile kernel (aec_net_tc_geometry out8[7] == 1; a unit = 128 tile sites, work-set sites and gaps alike); for a
+ * pool layer whose windows are partly evaluated inside the leak sweep (k_sweep_windows) the number of windows evaluated
+ * there (they are part of aec_net_read_counters' count for that layer); 0 for every other layer.  Reset together with aec_net_read_counters(reset = 1).
  */
 int aec_net_read_unit_counters(aec_net *net, unsigned long long *units, int n_layers);
 
