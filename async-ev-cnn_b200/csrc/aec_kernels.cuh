@@ -328,10 +328,10 @@ __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
     // leak + clamp (integration.py:63-68).  A pixel with S == 0 stays 0 and emits nothing, so only the pixels
     // alive after the previous step are touched: `al` starts as the previous alive bitmap and is walked one
     // word per warp, lane b owning bit b (coalesced over the set bits; the surface is mostly dead, so this
-    // reads a fraction of it), four words in flight per warp.
+    // reads a fraction of it), kU words in flight per warp.
     double *surf = p.surface + (long long)s * HW;
     const int lane = tid & 31, wid = tid >> 5;
-    constexpr int kWarps = kThreads / 32, kU = 4;
+    constexpr int kWarps = kThreads / 32, kU = 12;        // words in flight per warp: the walk is a chain of load latencies
     for (int w0 = wid; w0 < nbm; w0 += kWarps * kU) {
         uint32_t bits[kU];
         double v[kU];
@@ -941,8 +941,18 @@ struct FrontAllParams {
     const uint8_t *active;
 };
 
+// The layer table is copied to shared memory once per CTA: read from global memory layer by layer it cost one memory
+// round trip per layer on the CTA's critical path (the chain is latency-bound: one CTA walks every layer of its stream).
+constexpr int kMaxFrontLayers = 32;
+__device__ __forceinline__ void stage_front_table(FrontLayer *dst, const FrontLayer *src, int n_layers)
+{
+    const int words = n_layers * (int)(sizeof(FrontLayer) / 4);
+    for (int i = threadIdx.x; i < words; i += kThreads) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+}
+
 __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
 {
+    __shared__ __align__(16) FrontLayer s_layers[kMaxFrontLayers];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);        // previous layer's frontier
     uint32_t *bufB = bufA + p.max_words;                            // previous layer's non-zero-rate bits
@@ -951,9 +961,11 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
     uint32_t *Z = N + p.max_words;                                  // this layer's non-zero-rate bits
     __shared__ int scratch[9];
     const int s = blockIdx.x, tid = threadIdx.x;
+    stage_front_table(s_layers, p.layers, p.n_layers);
+    __syncthreads();
     if (!p.active[s]) {
         for (int li = 1; li < p.n_layers; ++li) {
-            const FrontLayer &L = p.layers[li];
+            const FrontLayer &L = s_layers[li];
             uint32_t *front = L.front + (long long)s * L.H * L.Ww;
             for (int i = tid; i < L.H * L.Ww; i += kThreads) front[i] = 0u;
         }
@@ -965,7 +977,7 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
     }
     __syncthreads();
     for (int li = 1; li < p.n_layers; ++li) {
-        const FrontLayer L = p.layers[li];
+        const FrontLayer &L = s_layers[li];
         const int nout = L.H * L.Ww;
         const uint32_t lastmask = (L.W & 31) ? ((1u << (L.W & 31)) - 1u) : 0xffffffffu;
         uint32_t *front = L.front + (long long)s * nout;
@@ -1102,12 +1114,14 @@ __global__ void __launch_bounds__(kThreads) k_frontier_skip(FrontAllParams p)
     uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);        // previous layer's (flip-free) frontier
     uint32_t *Hd = bufA + p.max_words;                              // scratch (horizontal dilation)
     uint32_t *N = Hd + p.max_words;                                 // this layer's set
+    __shared__ __align__(16) FrontLayer s_layers[kMaxFrontLayers];
     const int s = blockIdx.x, tid = threadIdx.x;
     if (!p.active[s]) return;                                       // the sweep does not touch an idle stream
+    stage_front_table(s_layers, p.layers, p.n_layers);
     for (int i = tid; i < p.words0; i += kThreads) bufA[i] = p.front0[(long long)s * p.words0 + i];
     __syncthreads();
     for (int li = 1; li < p.n_layers; ++li) {
-        const FrontLayer L = p.layers[li];
+        const FrontLayer &L = s_layers[li];
         const int nout = L.H * L.Ww;
         const uint32_t lastmask = (L.W & 31) ? ((1u << (L.W & 31)) - 1u) : 0xffffffffu;
         uint32_t *skip = L.skip + (long long)s * nout;
@@ -1304,6 +1318,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_eval(ConvEvalParams p)
     constexpr int TS = ROWS / 2;           // sites per tile
     constexpr int LDA = ROWS + 4;
     constexpr int LDB = BN + 4;
+    static_assert(sizeof(FrontLayer) % 4 == 0, "FrontLayer is copied word by word");
     static_assert(ROWS % 2 == 0 && TM <= TS && TS % TM == 0, "tile shape");
     __shared__ __align__(16) float As[BK][LDA];
     __shared__ __align__(16) float Bs[BK][LDB];
