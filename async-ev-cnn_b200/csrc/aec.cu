@@ -61,6 +61,8 @@ struct HostLayer {
     // tensor-core path (aec_tc.cuh): pre-split, pre-swizzled weight image and tile geometry
     bool tc = false;
     int KB = 0, Mrows = 0, Mch = 0, rep = 1, m_tiles = 0, mtu = 1, w_stages = 0, n_acc = 1, tc_blocks = 0;
+    bool pool_fuse = false;        // conv (gathered, weights-as-M): complete windows of the 2x2 pool behind it are evaluated in its epilogue
+    bool pool_in_conv = false;     // pool: ... by the conv layer in front of it
     bool tc_fast_decode = false;   // which site-decoder variant of k_conv_eval_tc the layer runs (fixed at finalize)
     bool tc_sm = false;            // sites-as-M form of the kernel (Cout <= 64, multiple of 4): aec_tc.cuh
     // row-tile form (aec_rt.cuh) of a sites-as-M layer: units of rt_R output rows x one x segment instead of single sites
@@ -581,7 +583,7 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
     return launch_check(n, "k_leak_sweep");
 }
 
-static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
+static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step)
 {
     HostLayer &l = n->L[li];
     const Src src = make_src(n, li - 1);
@@ -594,9 +596,21 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st)
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.Mch = l.Mch; p.rep = l.rep; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
+    p.quad_bit = 0u; p.site_counter = nullptr; p.pool_idx = nullptr; p.pool_Fp = p.pool_Ap = nullptr; p.pool_stride = 0; p.pool_flags = nullptr;
+    p.pool_accum = nullptr; p.pW = p.pWw = p.pHWw = 0; p.pool_alpha = 1.f;
 
     p.debug = n->tc_debug;
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
+    // the work list holds quads only when the fused step's frontier kernel wrote it (the layer-at-a-time interface and the
+    // dense initial forward emit plain lists and evaluate every pool window with k_pool_eval)
+    const bool pool = l.pool_fuse && fused_step;
+    if (pool) {
+        const HostLayer &pl = n->L[li + 1];
+        p.quad_bit = 0x80000000u; p.site_counter = n->counts + 32 + li;
+        p.pool_idx = pl.idx; p.pool_Fp = pl.Fp; p.pool_Ap = pl.Ap; p.pool_stride = pl.fstride; p.pool_flags = pl.flags;
+        p.pool_accum = n->accum + (li + 1); p.pW = pl.W; p.pWw = pl.Ww; p.pHWw = pl.H * pl.Ww; p.pool_alpha = l.alpha;
+        tc::k_conv_eval_tc<true, false, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    } else
     if (l.tc_sm) tc::k_conv_eval_tc<true, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else if (l.tc_fast_decode) tc::k_conv_eval_tc<true, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else tc::k_conv_eval_tc<false, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
@@ -639,7 +653,7 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = 
 {
     HostLayer &l = n->L[li];
     if (l.rt && fused_step) return run_conv_rows(n, li, st);
-    if (l.tc) return run_conv_eval_tc(n, li, st);
+    if (l.tc) return run_conv_eval_tc(n, li, st, fused_step);
     static const bool no_stencil = getenv("AEC_CONV_PATH") && strcmp(getenv("AEC_CONV_PATH"), "simt") == 0;
     if (n->L[li - 1].type == AEC_LAYER_INTEGRATION && l.C % 4 == 0 && l.C <= kStencilMaxC && l.kh * l.kw <= kStencilMaxK && !no_stencil) {
         StencilParams p;
@@ -817,6 +831,21 @@ extern "C" int aec_net_finalize(aec_net *n)
             pl.swp_fused = pl.kh == 2 && pl.kw == 2 && pl.stride == 2 && pl.C % 4 == 0;
         }
     }
+    {
+        // a 2x2 / stride-2 pool behind a conv layer on the gathered weights-as-M kernel: windows all four sites of which are
+        // re-evaluated are reduced in the conv epilogue (AEC_POOL_FUSE=0: never).  Needs a free bit in the work-list entries.
+        const char *e = getenv("AEC_POOL_FUSE");
+        for (size_t li = 1; li + 1 < n->L.size(); ++li) {
+            HostLayer &c = n->L[li], &pl = n->L[li + 1];
+            if (e && atoi(e) == 0) break;
+            if (c.type != AEC_LAYER_CONV || pl.type != AEC_LAYER_POOL || !c.tc || c.tc_sm || c.rt || c.rep != 1) continue;
+            if (!(pl.kh == 2 && pl.kw == 2 && pl.stride == 2) || pl.swp_fused) continue;
+            if (((unsigned long long)n->S << c.code.sh_s) > (1ULL << 31)) continue;
+            if ((unsigned long long)n->S * pl.H * pl.Ww >= (1ULL << 27)) continue;      // flag word index << 5 | bit in 32 bits
+            c.pool_fuse = true;
+            pl.pool_in_conv = true;
+        }
+    }
     if ((rc = dev_alloc(n, &n->surface, S * n->H * n->W, true))) return rc;
     if ((rc = dev_alloc(n, &n->delta, S, true))) return rc;
     if ((rc = dev_alloc(n, &n->prev_ts, S, true))) return rc;
@@ -894,6 +923,8 @@ extern "C" int aec_net_finalize(aec_net *n)
             f.front = l.front; f.signchg = l.signchg; f.flags = l.flags; f.nzr = l.nzr; f.skip = l.skip; f.sites = l.sites; f.counter = n->counts + li;
             f.rt_rows = l.rt ? l.rt_R : 0; f.rt_seg = l.rt_SEG; f.rt_nxg = l.rt_nxg; f.nset = l.nset; f.counter2 = n->counts + 32 + li;
             f.swp_uns = l.swp_fused ? l.swp_uns : nullptr; f.swp_skip = pv.skip;
+            f.quad_bit = l.pool_fuse ? 0x80000000u : 0u; f.pool_in_conv = l.pool_in_conv ? 1 : 0;
+            f.pWw = l.pool_fuse ? n->L[li + 1].Ww : 0;
             mw = std::max(mw, std::max(pv.H * pv.Ww, std::max(pv.H * l.Ww, l.H * l.Ww)));
         }
         n->front_max_words = mw;
@@ -961,12 +992,12 @@ extern "C" int aec_net_finalize(aec_net *n)
                 // decoder variant per layer (profiles/r1e_summary.md): the batched decoder pays for long units or several
                 // weight tiles; the environment is read here, once, not at every launch
                 const char *fk = getenv("AEC_TC_FASTDEC_KB");
-                l.tc_fast_decode = l.KB >= (fk ? atoi(fk) : 10) || (l.m_tiles > 1 && !fk);
+                l.tc_fast_decode = l.KB >= (fk ? atoi(fk) : 10) || (l.m_tiles > 1 && !fk) || l.pool_fuse;
             }
         if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
         if (tc_max) {
-            const void *variants[3] = {(const void *)tc::k_conv_eval_tc<false, false>, (const void *)tc::k_conv_eval_tc<true, false>,
-                                       (const void *)tc::k_conv_eval_tc<true, true>};
+            const void *variants[4] = {(const void *)tc::k_conv_eval_tc<false, false>, (const void *)tc::k_conv_eval_tc<true, false>,
+                                       (const void *)tc::k_conv_eval_tc<true, true>, (const void *)tc::k_conv_eval_tc<true, false, true>};
             for (const void *fn : variants) {
                 cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max);
                 if (e != cudaSuccess) return fail(AEC_ECUDA, "cannot opt in to %zu bytes of dynamic shared memory for the tensor-core conv kernel: %s", tc_max, cudaGetErrorString(e));
@@ -1418,7 +1449,7 @@ extern "C" int aec_net_read_unit_counters(aec_net *n, unsigned long long *units,
     CU(cudaDeviceSynchronize());
     unsigned long long tmp[64];
     CU(cudaMemcpy(tmp, n->accum, sizeof tmp, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n_layers && i < 31; ++i) units[i] = (i < (int)n->L.size() && (n->L[i].rt || n->L[i].swp_fused)) ? tmp[32 + i] : 0ULL;
+    for (int i = 0; i < n_layers && i < 31; ++i) units[i] = (i < (int)n->L.size() && (n->L[i].rt || n->L[i].swp_fused || n->L[i].pool_in_conv)) ? tmp[32 + i] : 0ULL;
     return AEC_OK;
 }
 

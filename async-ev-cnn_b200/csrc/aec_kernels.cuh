@@ -195,6 +195,76 @@ __device__ __forceinline__ void emit_sites(const uint32_t *bm, int H, int Ww, ui
     }
 }
 
+__device__ __forceinline__ uint32_t spread_to_pairs(uint32_t x)      // bit b of the low 16 bits -> bits 2b and 2b + 1
+{
+    x &= 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+
+// Work list of a conv layer whose 2x2 / stride-2 pool is evaluated in the conv kernel's epilogue (aec_tc.cuh, kPool): a pool
+// window ALL FOUR sites of which are in the work set (`quads`, a [H/2][pWw] bitmap over the windows) is emitted as four
+// consecutive entries in the window's row order (0,0) (0,1) (1,0) (1,1), the first carrying `quad_bit`; the epilogue thread
+// that owns a channel then has the window's four values in adjacent accumulator columns.  All quads of the stream come first,
+// then the remaining sites row-major, then 0xffffffff entries up to a multiple of four: every stream's block starts on a
+// multiple of four, so a quad never straddles two 128-entry units.  *site_counter counts the real sites.
+__device__ __forceinline__ void emit_sites_quads(const uint32_t *bm, const uint32_t *quads, int H, int Ww, int pWw, uint32_t base_id, int sh_y,
+                                                 uint32_t quad_bit, uint32_t *sites, int *counter, int *site_counter, int *scratch)
+{
+    const int nwords = H * Ww, pwords = (H >> 1) * pWw;
+    const int per = (nwords + kThreads - 1) / kThreads, pper = (pwords + kThreads - 1) / kThreads;
+    const int w0 = threadIdx.x * per, w1 = min(nwords, w0 + per);
+    const int q0 = threadIdx.x * pper, q1 = min(pwords, q0 + pper);
+    auto singles = [&](int w) {
+        const int y = w / Ww, xw = w - y * Ww;
+        return bm[w] & ~spread_to_pairs(quads[(y >> 1) * pWw + (xw >> 1)] >> ((xw & 1) * 16));
+    };
+    int cq = 0, cs = 0;
+    for (int q = q0; q < q1; ++q) cq += __popc(quads[q]);
+    for (int w = w0; w < w1; ++w) cs += __popc(singles(w));
+    int total_q, total_s;
+    int off_q = block_excl_scan(cq, scratch, &total_q);
+    int off_s = block_excl_scan(cs, scratch, &total_s);
+    const int pad = (4 - (total_s & 3)) & 3;
+    __shared__ int s_qbase;
+    if (threadIdx.x == 0) {
+        const int total = 4 * total_q + total_s;
+        s_qbase = total > 0 ? atomicAdd(counter, total + pad) : 0;
+        if (total > 0) atomicAdd(site_counter, total);
+    }
+    __syncthreads();
+    off_q = s_qbase + 4 * off_q;
+    off_s += s_qbase + 4 * total_q;
+    for (int q = q0; q < q1; ++q) {
+        uint32_t bits = quads[q];
+        const int oy = q / pWw, xb = (q - oy * pWw) * 32;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t e = base_id | ((uint32_t)(2 * oy) << sh_y) | (uint32_t)(2 * (xb + b));
+            sites[off_q] = e | quad_bit;
+            sites[off_q + 1] = e + 1u;
+            sites[off_q + 2] = e + (1u << sh_y);
+            sites[off_q + 3] = e + (1u << sh_y) + 1u;
+            off_q += 4;
+        }
+    }
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = singles(w);
+        const int y = w / Ww, xb = (w - y * Ww) * 32;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            sites[off_s++] = base_id | ((uint32_t)y << sh_y) | (uint32_t)(xb + b);
+        }
+    }
+    if (threadIdx.x == 0)
+        for (int i = 0; i < pad; ++i) sites[s_qbase + 4 * total_q + total_s + i] = 0xffffffffu;
+}
+
 // Row-tile layers: emits one entry per unit (rt_rows output rows x one x segment) that holds a work-set bit,
 // entry = base_id | row group << sh_y | segment, in (row group, segment) order.
 __device__ __forceinline__ void emit_units(const uint32_t *bm, int H, int W, int Ww, int rows, int seg, int nxg, uint32_t base_id, int sh_y,
@@ -926,7 +996,10 @@ struct FrontLayer {
     uint32_t *nset;               // row-tile layer: [S][H*Ww] copy of the exact work set (the evaluation stores only there)
     uint32_t *swp_uns;            // pool layer whose sticky windows the leak sweep evaluates (SweepPool): their unstable bits, else null
     const uint32_t *swp_skip;     // ... and the conv layer's skip bitmap (= its exact work set: first conv layer only)
-    int *counter2;                // row-tile layer: number of work-set sites (statistics)
+    int *counter2;                // row-tile layer / conv layer with a fused pool: number of work-set sites (statistics)
+    uint32_t quad_bit;            // conv layer whose pool is evaluated in its epilogue (emit_sites_quads): the entry flag; else 0
+    int pool_in_conv;             // pool layer: 1 = the windows all four sites of which the conv re-evaluates are evaluated by the conv kernel
+    int pWw;                      // conv layer with quad_bit: bitmap words per row of the pool layer behind it
     uint32_t *front, *signchg, *flags, *nzr;
     uint32_t *skip;               // [S][H*Ww] written by k_frontier_skip: a subset of this step's work set, known before the leak sweep
     uint32_t *sites;
@@ -1056,6 +1129,7 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
                 uint32_t f = before & ~hit;           // maxpool.py:118-120
                 const uint32_t wset = hit | f;        // maxpool.py:123-126
                 uint32_t todo = wset;                 // windows k_pool_eval has to evaluate
+                if (L.pool_in_conv) todo &= ~Hd[i];   // complete windows: the conv epilogue evaluates them (Hd = their bitmap, from the conv layer's pass)
                 if (uns) {
                     // windows the leak sweep has evaluated already (sticky flag set, none of their conv sites re-evaluated): they
                     // stay output events of the layer but leave the work list; a window among them that was hit after all (by a
@@ -1081,7 +1155,21 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
             __syncthreads();
             continue;
         }
-        if (L.type == 1 && L.rt_rows > 0) {
+        if (L.type == 1 && L.quad_bit) {
+            // the pool behind this layer is evaluated in the conv epilogue for complete windows: Hd (free now) = those windows
+            const int pwords = (L.H >> 1) * L.pWw;
+            for (int i = tid; i < pwords; i += kThreads) {
+                const int oy = i / L.pWw, w = i - oy * L.pWw;
+                const uint32_t *r0 = N + (2 * oy) * L.Ww, *r1 = r0 + L.Ww;
+                uint32_t lo = (2 * w < L.Ww) ? (r0[2 * w] & r1[2 * w]) : 0u;
+                uint32_t hi = (2 * w + 1 < L.Ww) ? (r0[2 * w + 1] & r1[2 * w + 1]) : 0u;
+                lo &= lo >> 1;
+                hi &= hi >> 1;
+                Hd[i] = compress_even_bits(lo) | (compress_even_bits(hi) << 16);
+            }
+            __syncthreads();
+            emit_sites_quads(N, Hd, L.H, L.Ww, L.pWw, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.quad_bit, L.sites, L.counter, L.counter2, scratch);
+        } else if (L.type == 1 && L.rt_rows > 0) {
             // row-tile conv layer: the evaluation needs the work set itself (it stores only there) and one entry per active unit
             uint32_t *ns = L.nset + (long long)s * nout;
             int cnt = 0;

@@ -166,6 +166,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 // True in exactly one lane of a converged warp.  The MMA / loader warps run their loops converged on
 // warp-uniform values and guard only the issuing instructions with this, so ptxas keeps descriptors
 // in uniform registers and emits back-to-back UTCHMMA (a `lane == 0` branch around the whole loop
@@ -211,6 +217,17 @@ struct TcParams {
     SiteCode code;              // work-list entry coding of the output layer
     int w_stages;               // weight pipeline depth
     int n_acc;                  // accumulator buffers in TMEM (2 when mtu == 1, else 1)
+    // kPool (weights-as-M only): the 2x2 / stride-2 pool behind this layer is evaluated here for the windows that arrive as quads
+    // (four consecutive work-list entries, the first flagged with quad_bit: emit_sites_quads) - maxpool.py:130-151, cutils.pyx:161-177
+    uint32_t quad_bit;
+    const int *site_counter;    // real work-set sites (the list also holds padding entries)
+    uint8_t *pool_idx;          // [S][pool_stride] argmax rows
+    float *pool_Fp, *pool_Ap;   // [S][pool_stride] (F, A) copies at the argmax
+    long long pool_stride;
+    uint32_t *pool_flags;       // [S][pHWw] sticky recompute flags: set where a window comes out unstable
+    unsigned long long *pool_accum;   // the pool layer's work counter; [32] behind it: windows evaluated here
+    int pW, pWw, pHWw;
+    float pool_alpha;           // this layer's activation slope (the pool ranks rates R = A * slope(F))
     unsigned long long *timing; // null, or 16 cycle counters accumulated over CTAs (aec_net_tc_timing): see TcTimingSlot
     int debug;                  // AEC_TC_DEBUG experiment bits (results invalid when non-zero): 1 no gather loads, 2 no operand stores, 4 no MMA, 8 no epilogue stores, 16 no weight copies
 };
@@ -329,9 +346,10 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
 // The weight stages come first: the A descriptor always spans 128 rows, so with Mrows < 128 it reads
 // past the tile into whatever follows (the next stage / the site stages); those rows only feed
 // accumulator lanes >= Mrows, which the epilogue never reads.
-template <bool kFastDecode, bool kSM>
+template <bool kFastDecode, bool kSM, bool kPool = false>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
+    static_assert(!kPool || (kFastDecode && !kSM), "the fused pool lives in the weights-as-M epilogue and the batched decoder");
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ __align__(8) uint64_t bar_x_full[kSiteStages], bar_x_empty[kSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[kSiteRing], bar_si_free[kSiteRing];
@@ -339,10 +357,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     __shared__ __align__(16) SiteSrc s_src[kSiteRing][kUnitSites];
     __shared__ __align__(16) long long s_dst[kSiteRing][kUnitSites];   // byte offset of the site's channel 0 in F (and in A)
     __shared__ KEntry s_ktab[kKtabBlocks * 8];
+    // kPool: per group of four entries, the pool window they form (element offset of its channel 0 in idx / Fp / Ap, -1: not a
+    // quad) and where its recompute flag lives (word << 5 | bit)
+    __shared__ long long s_pool[kPool ? kSiteRing : 1][kPool ? kUnitSites / 4 : 1];
+    __shared__ uint32_t s_pflag[kPool ? kSiteRing : 1][kPool ? kUnitSites / 4 : 1];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_sites = __shfl_sync(0xffffffffu, *p.counter, 0);      // warp-uniform for the compiler's sake
-    if (blockIdx.x == 0 && tid == 0 && n_sites > 0) atomicAdd(p.accum, (unsigned long long)n_sites);
+    if (blockIdx.x == 0 && tid == 0 && n_sites > 0) atomicAdd(p.accum, (unsigned long long)(kPool ? *p.site_counter : n_sites));
     const int n_blocks = (n_sites + kUnitSites - 1) / kUnitSites;
     const int n_mgroups = (p.m_tiles + p.mtu - 1) / p.mtu;
     const int total_units = n_blocks * n_mgroups;
@@ -391,6 +413,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         const bool warp_live = warp * 32 < p.Mrows;          // warps whose 32 lanes hold no channel only arrive
         long long tw_acc = 0, tw_si = 0;
+        int n_quads = 0;                                     // kPool: windows evaluated here (counted once, by the first weight tile's CTA)
         const long long t_begin = timing ? clock64() : 0;
         for (int ul = 0; ul < n_units_cta; ++ul) {
             const int unit = blockIdx.x + ul * gridDim.x;
@@ -447,6 +470,94 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     if (ci + 2 < total) issue(ci + 2, ra, rb);
                     emit(ci + 1, rc, rd);
                 }
+            } else if constexpr (kPool) {
+              if (warp_live) {
+                // Weights-as-M with the pool fused: thread = channel, 8 sites (two possible windows) per step - their value
+                // columns and the rate columns 64 further on - so that a quad's four (F, A) pairs are in registers together.
+                // The list may hold padding entries anywhere (end of a stream's block): every site is checked by its own offset.
+                for (int mt = 0; mt < mt_count; ++mt) {
+                    const int c = (mg * p.mtu + mt) * p.Mch + row;
+                    const bool c_ok = row < p.Mrows && c < p.C && !(p.debug & 8);
+                    const long long a_minus_f = (const char *)p.A - (const char *)p.F;
+                    const float bias = c_ok ? __ldg(p.bias + c) : 0.f;
+                    const uint32_t taddr = lane_addr + (uint32_t)((ab * p.mtu + mt) * kUnitCols);
+                    char *const baseF = (char *)p.F + (long long)c * 4;
+                    uint32_t va[8], ra[8], vb[8], rb[8];
+                    auto issue = [&](int g8, uint32_t(&v)[8], uint32_t(&r)[8]) {
+                        const uint32_t cc = (uint32_t)((g8 >> 3) * 128 + (g8 & 7) * 8);     // item (g8 >> 3): 64 value columns, then 64 rate columns
+                        tmem_ld8(taddr + cc, v);
+                        tmem_ld8(taddr + cc + 64u, r);
+                    };
+                    auto emit = [&](int g8, const uint32_t(&v)[8], const uint32_t(&r)[8]) {
+                        const int i0 = g8 * 8;
+                        const longlong2 *po = reinterpret_cast<const longlong2 *>(&s_dst[buf][i0]);
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const longlong2 o = po[e];
+                            f[2 * e] = __fadd_rn(__uint_as_float(v[2 * e]), bias);
+                            f[2 * e + 1] = __fadd_rn(__uint_as_float(v[2 * e + 1]), bias);
+                            if (c_ok && o.x >= 0) {
+                                *reinterpret_cast<float *>(baseF + o.x) = f[2 * e];
+                                *reinterpret_cast<float *>(baseF + a_minus_f + o.x) = __uint_as_float(r[2 * e]);
+                            }
+                            if (c_ok && o.y >= 0) {
+                                *reinterpret_cast<float *>(baseF + o.y) = f[2 * e + 1];
+                                *reinterpret_cast<float *>(baseF + a_minus_f + o.y) = __uint_as_float(r[2 * e + 1]);
+                            }
+                        }
+                        // Both possible windows of the group branch-free (the epilogue warp shares its scheduler with three producer
+                        // warps and runs one dependent chain: what it needs is independent instructions, not fewer of them).
+                        // Winner by tournament with the reference's order (cutils.pyx:166-170: larger F, then smaller rate, then the
+                        // earlier row): (0,1), (2,3), then the two winners - the first maximal element, like the sequential scan.
+                        long long pw[2];
+                        bool uns[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            pw[q] = s_pool[buf][(i0 >> 2) + q];
+                            float rr[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) rr[k] = __fmul_rn(__uint_as_float(r[4 * q + k]), slope_of(f[4 * q + k], p.pool_alpha));
+                            const bool b1 = f[4 * q + 1] > f[4 * q] || (f[4 * q + 1] == f[4 * q] && rr[1] < rr[0]);
+                            const bool b3 = f[4 * q + 3] > f[4 * q + 2] || (f[4 * q + 3] == f[4 * q + 2] && rr[3] < rr[2]);
+                            const float fa = b1 ? f[4 * q + 1] : f[4 * q], ra_ = b1 ? rr[1] : rr[0];
+                            const float fb = b3 ? f[4 * q + 3] : f[4 * q + 2], rb_ = b3 ? rr[3] : rr[2];
+                            const uint32_t aa = b1 ? r[4 * q + 1] : r[4 * q], ab_ = b3 ? r[4 * q + 3] : r[4 * q + 2];
+                            const bool bb = fb > fa || (fb == fa && rb_ < ra_);
+                            const int row_best = bb ? (b3 ? 3 : 2) : (b1 ? 1 : 0);
+                            const float f_best = bb ? fb : fa, r_best = bb ? rb_ : ra_;
+                            const uint32_t a_best = bb ? ab_ : aa;
+                            const float rlow = fminf(fminf(rr[0], rr[1]), fminf(rr[2], rr[3]));
+                            const bool ok = c_ok && pw[q] >= 0;
+                            uns[q] = ok && r_best != rlow;                                   // cutils.pyx:173-177 (by value)
+                            if (ok) {
+                                p.pool_idx[pw[q] + c] = (uint8_t)row_best;
+                                p.pool_Fp[pw[q] + c] = f_best;
+                                p.pool_Ap[pw[q] + c] = __uint_as_float(a_best);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const unsigned any = __ballot_sync(0xffffffffu, uns[q]);
+                            if (any && lane == 0) {
+                                const uint32_t code = s_pflag[buf][(i0 >> 2) + q];
+                                atomicOr(p.pool_flags + (code >> 5), 1u << (code & 31u));
+                            }
+                            if (pw[q] >= 0 && mt == 0 && mg * p.mtu == 0 && warp == 0 && lane == 0) ++n_quads;
+                        }
+                    };
+                    issue(0, va, ra);
+#pragma unroll 1
+                    for (int g8 = 0; g8 < kUnitSites / 8; g8 += 2) {
+                        tmem_ld_wait();
+                        issue(g8 + 1, vb, rb);
+                        emit(g8, va, ra);
+                        tmem_ld_wait();
+                        if (g8 + 2 < kUnitSites / 8) issue(g8 + 2, va, ra);
+                        emit(g8 + 1, vb, rb);
+                    }
+                }
+              }
             } else
             if (warp_live) {
                 for (int mt = 0; mt < mt_count; ++mt) {
@@ -490,6 +601,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             tc_fence_before();
             mbar_arrive(smem_u32(&bar_acc_empty[ab]));
             mbar_arrive(smem_u32(&bar_si_free[buf]));
+        }
+        if constexpr (kPool) {
+            if (n_quads > 0) { atomicAdd(p.pool_accum, (unsigned long long)n_quads); atomicAdd(p.pool_accum + 32, (unsigned long long)n_quads); }
         }
         if (timing && tid == 0) {
             atomicAdd(p.timing + kTEpiTotal, (unsigned long long)(clock64() - t_begin));
@@ -662,10 +776,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     SiteSrc q;
                     q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
                     long long dst = -1;
+                    if constexpr (kPool) {
+                        if ((i & 3) == 0) { s_pool[buf][i >> 2] = -1; s_pflag[buf][i >> 2] = 0u; }
+                    }
                     if (ent[k] != 0xffffffffu) {
                         int s, y, x;
-                        site_decode(p.code, ent[k], s, y, x);
+                        site_decode(p.code, kPool ? ent[k] & ~p.quad_bit : ent[k], s, y, x);
                         const int site = y * p.W + x;
+                        if constexpr (kPool) {
+                            if (ent[k] & p.quad_bit) {          // first entry of a complete window: (y, x) is its top-left site
+                                const int oy = y >> 1, ox = x >> 1;
+                                s_pool[buf][i >> 2] = (long long)s * p.pool_stride + (long long)(oy * p.pW + ox) * p.C;
+                                s_pflag[buf][i >> 2] = ((uint32_t)(s * p.pHWw + oy * p.pWw + (ox >> 5)) << 5) | (uint32_t)(ox & 31);
+                            }
+                        }
                         q.ptr = reinterpret_cast<const char *>(p.srcF + ((long long)s * p.src_stride + (long long)(y * p.Win + x) * p.Cin));
                         uint32_t colbits = 0u;
                         for (int kx = 0; kx < p.kw; ++kx)

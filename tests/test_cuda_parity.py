@@ -452,3 +452,69 @@ def test_sweep_skipping_changes_no_bit(monkeypatch):
     assert nets[1].sweep_stats()["swept_conv_elems"] == nets[1].sweep_stats()["live_conv_elems"]
     for n in nets:
         n.close()
+
+
+POOL_IN_CONV = "conv1=3,3,1,16 pool1=2,2 conv2=3,3,16,96 pool2=2,2 conv3=3,3,96,160 pool3=2,2 conv4=1,1,160,12"
+
+
+def test_pool_in_conv_epilogue_exact():
+    """Conv layers with more than 64 channels run on the gathered weights-as-M kernel, whose epilogue evaluates the 2x2 pool
+    behind them for the windows all four sites of which are re-evaluated (work list ordered by window, aec_tc.cuh kPool;
+    the rest of the pool's work set stays with k_pool_eval).  One weight tile (96 channels) and two (160); exactly
+    representable arithmetic -> maps, argmax rows, copies, flags and frontiers bit-equal to the oracle
+    (maxpool.py:118-151, cutils.pyx:161-177)."""
+    S, steps, h, w = 5, 50, 32, 48
+    wts = P.xavier_weights(POOL_IN_CONV, seed=21, exact=True)
+    evs = P.synthetic_events("edge", S, steps, 24, h, w, seed=23, dt_int=(1, 5))
+    net = EventNetCuda(h, w, POOL_IN_CONV, wts, 1.0 / 64, 0.5, "SAME", n_streams=S)
+    oracles = [OracleEventNet(h, w, POOL_IN_CONV, wts, 1.0 / 64, 0.5, "SAME") for _ in range(S)]
+    for t in range(steps):
+        per = [evs[s, t] if (s + 2 * t) % 7 else None for s in range(S)]
+        heads = net.step(per)
+        for s in range(S):
+            if per[s] is None:
+                continue
+            assert np.array_equal(heads[s], oracles[s].step(per[s])), "step %d stream %d head" % (t, s)
+        if t % 5 == 4:
+            for s in range(S):
+                oa = OracleAdapter(oracles[s])
+                for i in range(len(net.names)):
+                    so, sc = oa.state(i), net.state(i, s)
+                    for key in so:
+                        assert np.array_equal(sc[key], so[key]), "step %d stream %d layer %s %s" % (t, s, net.names[i], key)
+                    if per[s] is not None:
+                        assert np.array_equal(net.frontier(i, s), oa.frontier(i))
+    units = net.unit_counters()
+    names = list(net.names)
+    assert units[names.index("pool2")] > 0 and units[names.index("pool3")] > 0, "no window was evaluated in a conv epilogue"
+    net.close()
+
+
+def test_pool_in_conv_epilogue_changes_no_bit(monkeypatch):
+    """The same float net with the fusion on and off (AEC_POOL_FUSE=0: every pool window goes through k_pool_eval): heads,
+    maps, argmax rows, (Fp, Ap) copies, flags and frontiers must be bit-identical, and the per-layer work counters equal."""
+    S, steps, h, w = 3, 80, 32, 48
+    wts = P.xavier_weights(POOL_IN_CONV, seed=4)
+    evs = P.synthetic_events("edge", S, steps, 30, h, w, seed=8)
+    nets = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AEC_POOL_FUSE", flag)
+        nets.append(EventNetCuda(h, w, POOL_IN_CONV, wts, 5e-5, 0.1, "SAME", n_streams=S))
+    for t in range(steps):
+        per = [evs[s, t] if (s + t) % 4 else None for s in range(S)]
+        ha, hb = nets[0].step(per), nets[1].step(per)
+        assert np.array_equal(ha, hb), "step %d head" % t
+        if t % 8 == 7 or t == steps - 1:
+            for s in range(S):
+                for i in range(len(nets[0].names)):
+                    sa, sb = nets[0].state(i, s), nets[1].state(i, s)
+                    for key in sa:
+                        assert np.array_equal(sa[key], sb[key]), "step %d stream %d layer %s %s" % (t, s, nets[0].names[i], key)
+                    assert np.array_equal(nets[0].frontier(i, s), nets[1].frontier(i, s))
+    ca, cb = nets[0].counters()[0], nets[1].counters()[0]
+    assert np.array_equal(ca, cb), (ca, cb)
+    names = list(nets[0].names)
+    for nm in ("pool2", "pool3"):
+        assert nets[0].unit_counters()[names.index(nm)] > 0 and nets[1].unit_counters()[names.index(nm)] == 0
+    for n in nets:
+        n.close()
