@@ -347,6 +347,12 @@ static void build_rt_image(HostLayer &l, const float *kernel_hwio)
     if (l.rt_wres) {
         l.rt_wst = l.kh * l.kw * l.rt_ncb;
         l.rt_xst = all_w + 3 * 4 * l.rt_xtile <= budget ? 3 : 2;
+        // a fourth site stage and producer group where they fit (64-byte rows with resident weights: EFCN conv2)
+        const char *g4 = getenv("AEC_RT_GROUPS4");
+        if (!(g4 && atoi(g4) == 0) && l.rt_groups == 3 && all_w + 4 * 4 * l.rt_xtile <= budget && (n_pairs + 95) / 96 <= rt::kRtMaxPairs) {
+            l.rt_xst = 4;
+            l.rt_groups = 4;
+        }
     } else {
         l.rt_xst = 4 * l.rt_xtile * 3 + (size_t)(l.kw + 2) * l.rt_wtile <= budget ? 3 : 2;
         l.rt_wst = (int)std::min<size_t>(rt::kRtMaxWStages, (budget - (size_t)l.rt_xst * 4 * l.rt_xtile) / l.rt_wtile);
@@ -635,6 +641,10 @@ static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l;
     p.CB = l.rt_CB; p.ncb = l.rt_ncb; p.row_bytes = l.rt_CB * 4;
     p.R = l.rt_R; p.sw_shift = l.rt_sw_shift; p.SEG = l.rt_SEG; p.code = l.code; p.P = l.rt_P;
+    {
+        static const bool no32 = getenv("AEC_RT_STORE32") && atoi(getenv("AEC_RT_STORE32")) == 0;
+        p.store32 = (!no32 && l.C % 8 == 0 && l.fstride % 8 == 0 && ((uintptr_t)l.F % 32) == 0 && ((uintptr_t)l.A % 32) == 0) ? 1 : 0;
+    }
     p.x_tile_bytes = (uint32_t)l.rt_xtile; p.w_tile_bytes = (uint32_t)l.rt_wtile; p.x_stages = l.rt_xst; p.w_stages = l.rt_wst; p.w_resident = l.rt_wres ? 1 : 0;
     p.debug = n->tc_debug;
     p.prod_groups = l.rt_groups;

@@ -30,7 +30,7 @@ namespace rt {
 
 using namespace tc;
 
-constexpr int kRtMaxXStages = 3;
+constexpr int kRtMaxXStages = 4;
 constexpr int kRtMaxWStages = 6;
 constexpr int kRtRing = 4;            // unit-info buffers
 constexpr int kRtProdThreads = kGroups * kGroupThreads;   // 384
@@ -72,6 +72,7 @@ struct RtParams {
     uint32_t w_tile_bytes;      // 2 * Cpad * row_bytes
     int x_stages, w_stages;     // w_stages: weight tile slots; w_resident: every tile has its own slot, loaded once per CTA
     int w_resident;
+    int store32;                // direct epilogue stores as 32-byte st.global.v8 (C % 8 == 0 and 32-byte aligned site rows)
     int debug;
     int prod_groups;            // the 12 producer warps work as 2 or 3 groups; group g fills the stages q = g, g + G, ...
     unsigned long long *timing; // null, or the 16 role cycle counters of aec_net_tc_timing (TcTimingSlot)
@@ -223,19 +224,35 @@ __global__ void __launch_bounds__(kRtThreads, 1) k_conv_rows(const __grid_consta
                 if (!staged) {
                     if (!site_ok) return;
                     char *const out = (char *)(map ? p.A : p.F) + dst + (long long)c0 * 4;
+                    float4 o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        o[q].x = __fadd_rn(__uint_as_float(hi[4 * q + 0]), __uint_as_float(lo[4 * q + 0]));
+                        o[q].y = __fadd_rn(__uint_as_float(hi[4 * q + 1]), __uint_as_float(lo[4 * q + 1]));
+                        o[q].z = __fadd_rn(__uint_as_float(hi[4 * q + 2]), __uint_as_float(lo[4 * q + 2]));
+                        o[q].w = __fadd_rn(__uint_as_float(hi[4 * q + 3]), __uint_as_float(lo[4 * q + 3]));
+                        if (!map && c0 + 4 * q < p.C) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + 4 * q));
+                            o[q].x = __fadd_rn(o[q].x, b.x); o[q].y = __fadd_rn(o[q].y, b.y); o[q].z = __fadd_rn(o[q].z, b.z); o[q].w = __fadd_rn(o[q].w, b.w);
+                        }
+                    }
+                    if (p.store32) {
+                        // One thread = one site: a 16-byte store per thread is 32 half sectors of 32 different rows per instruction,
+                        // and the memory system takes ~0.65 sector requests per cycle and SM whether half or full
+                        // (tools/bench_store.cu: 10 B/cycle/SM against 20.5 with st.global.v8 = STG.256, full 32-byte sectors).
+#pragma unroll
+                        for (int q = 0; q < 4; q += 2) {
+                            if (c0 + 4 * q >= p.C) break;                       // C % 8 == 0 on this path
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + 16 * q), "f"(o[q].x), "f"(o[q].y), "f"(o[q].z),
+                                         "f"(o[q].w), "f"(o[q + 1].x), "f"(o[q + 1].y), "f"(o[q + 1].z), "f"(o[q + 1].w)
+                                         : "memory");
+                        }
+                        return;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         if (c0 + 4 * q >= p.C) break;
-                        float4 o;
-                        o.x = __fadd_rn(__uint_as_float(hi[4 * q + 0]), __uint_as_float(lo[4 * q + 0]));
-                        o.y = __fadd_rn(__uint_as_float(hi[4 * q + 1]), __uint_as_float(lo[4 * q + 1]));
-                        o.z = __fadd_rn(__uint_as_float(hi[4 * q + 2]), __uint_as_float(lo[4 * q + 2]));
-                        o.w = __fadd_rn(__uint_as_float(hi[4 * q + 3]), __uint_as_float(lo[4 * q + 3]));
-                        if (!map) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + 4 * q));
-                            o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
-                        }
-                        *reinterpret_cast<float4 *>(out + 16 * q) = o;
+                        *reinterpret_cast<float4 *>(out + 16 * q) = o[q];
                     }
                     return;
                 }

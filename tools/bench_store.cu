@@ -4,6 +4,9 @@
 //   mode 1  st.global.v4.b32, lane = (row, 16-byte piece): one instruction = 32 pieces of 32 different rows (sites-as-M, direct)
 //   mode 2  st.global.v4.b32, 8 lanes = one 128-byte run (transposed through shared memory beforehand; the transpose is not timed)
 //   mode 3  cp.async.bulk shared -> global, one bulk copy per row issued by lane 0 of each warp (the rows staged in shared memory)
+//   mode 4  st.global.v2.b32, 4 lanes = one 32-byte sector of a row, 8 rows per instruction (the tcgen05.ld.16x256b register layout)
+//   mode 5  st.global.v4.b32, 2 lanes = one 32-byte sector of a row, 16 rows per instruction
+//   mode 6  st.global.v8.f32 (STG.256), lane = row: 32 full sectors of 32 different rows per instruction
 // All 148 CTAs write disjoint regions of a 1 GB buffer; rows are visited in a hashed order.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bench_store.bin tools/bench_store.cu
 #include <cstdio>
@@ -34,6 +37,21 @@ __global__ void __launch_bounds__(1024, 1) k_store(char *buf, long long region, 
             char *d2 = base + (size_t)((row + (uint32_t)lane) & row_mask) * (uint32_t)row_bytes;
             for (int c = 0; c < row_bytes; c += 16) *reinterpret_cast<float4 *>(d2 + c) = make_float4(v, v, v, v);
             r += 31;
+        } else if (mode == 4) {
+            // 8 different rows per instruction, 4 lanes = one full 32-byte sector of a row (the tcgen05.ld.16x256b register layout)
+            char *d2 = base + (size_t)((row + (uint32_t)(lane >> 2)) & row_mask) * (uint32_t)row_bytes + (lane & 3) * 8;
+            for (int c = 0; c < row_bytes; c += 32) *reinterpret_cast<float2 *>(d2 + c) = make_float2(v, v);
+            r += 7;
+        } else if (mode == 5) {
+            // 16 different rows per instruction, 2 lanes = one 32-byte sector (st.v4)
+            char *d2 = base + (size_t)((row + (uint32_t)(lane >> 1)) & row_mask) * (uint32_t)row_bytes + (lane & 1) * 16;
+            for (int c = 0; c < row_bytes; c += 32) *reinterpret_cast<float4 *>(d2 + c) = make_float4(v, v, v, v);
+            r += 15;
+        } else if (mode == 6) {
+            // 32 different rows per instruction, every lane one full 32-byte sector (st.global.v8.f32 = STG.256, sm_100)
+            char *d2 = base + (size_t)((row + (uint32_t)lane) & row_mask) * (uint32_t)row_bytes;
+            for (int c = 0; c < row_bytes; c += 32) asm volatile("st.global.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(d2 + c), "f"(v) : "memory");
+            r += 31;
         } else if (mode == 2) {
             for (int c = lane * 16; c < row_bytes; c += 512) *reinterpret_cast<float4 *>(dst + c) = make_float4(v, v, v, v);
         } else {
@@ -58,9 +76,10 @@ int main()
     cudaMalloc(&buf, 148 * region);
     cudaMalloc(&out, 148 * sizeof(long long));
     cudaFuncSetAttribute(k_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
-    const char *names[4] = {"st.b32 lane=channel (128 B runs)", "st.v4 lane=row (32 rows/instr)", "st.v4 8+ lanes per row (512 B/instr)", "cp.async.bulk per row"};
+    const char *names[7] = {"st.b32 lane=channel (128 B runs)", "st.v4 lane=row (32 rows/instr)", "st.v4 8+ lanes per row (512 B/instr)", "cp.async.bulk per row",
+                            "st.v2 4 lanes = 32 B (8 rows/instr)", "st.v4 2 lanes = 32 B (16 rows/instr)", "st.v8 lane=row (32 rows x 32 B/instr)"};
     for (int row_bytes : {128, 256, 512})
-        for (int mode = 0; mode < 4; ++mode)
+        for (int mode = 0; mode < 7; ++mode)
             for (int warps : {4, 8, 16}) {
                 const int rows_per_warp = 8192 * 4 / warps;
                 for (int rep = 0; rep < 2; ++rep) {
