@@ -96,6 +96,7 @@ struct aec_net {
     uint8_t *active = nullptr, *mask = nullptr;
     uint32_t *sites = nullptr;
     bool sweep_skip = true;              // the leak sweep leaves the sites alone that the step re-evaluates (AEC_SWEEP_SKIP=0: leak every live site)
+    bool tc_half = true, rt_store32 = true;   // developer switches read at finalize (AEC_TC_HALF, AEC_RT_STORE32)
     FrontLayer *front_table = nullptr;   // device copy of the per-layer frontier descriptors (k_frontier_all)
     int front_max_words = 0;
     int *counts = nullptr, *err_flag = nullptr;
@@ -602,6 +603,7 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.Mch = l.Mch; p.rep = l.rep; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
+    p.half_units = n->tc_half ? 1 : 0;
     p.quad_bit = 0u; p.site_counter = nullptr; p.pool_idx = nullptr; p.pool_Fp = p.pool_Ap = nullptr; p.pool_stride = 0; p.pool_flags = nullptr;
     p.pool_accum = nullptr; p.pW = p.pWw = p.pHWw = 0; p.pool_alpha = 1.f;
 
@@ -642,8 +644,7 @@ static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
     p.CB = l.rt_CB; p.ncb = l.rt_ncb; p.row_bytes = l.rt_CB * 4;
     p.R = l.rt_R; p.sw_shift = l.rt_sw_shift; p.SEG = l.rt_SEG; p.code = l.code; p.P = l.rt_P;
     {
-        static const bool no32 = getenv("AEC_RT_STORE32") && atoi(getenv("AEC_RT_STORE32")) == 0;
-        p.store32 = (!no32 && l.C % 8 == 0 && l.fstride % 8 == 0 && ((uintptr_t)l.F % 32) == 0 && ((uintptr_t)l.A % 32) == 0) ? 1 : 0;
+        p.store32 = (n->rt_store32 && l.C % 8 == 0 && l.fstride % 8 == 0 && ((uintptr_t)l.F % 32) == 0 && ((uintptr_t)l.A % 32) == 0) ? 1 : 0;
     }
     p.x_tile_bytes = (uint32_t)l.rt_xtile; p.w_tile_bytes = (uint32_t)l.rt_wtile; p.x_stages = l.rt_xst; p.w_stages = l.rt_wst; p.w_resident = l.rt_wres ? 1 : 0;
     p.debug = n->tc_debug;
@@ -947,6 +948,8 @@ extern "C" int aec_net_finalize(aec_net *n)
 
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
     { const char *e = getenv("AEC_TC_DEBUG"); n->tc_debug = e ? atoi(e) : 0; }
+    { const char *e = getenv("AEC_TC_HALF"); n->tc_half = !(e && atoi(e) == 0); }            // 64-site units for small work lists (aec_tc.cuh)
+    { const char *e = getenv("AEC_RT_STORE32"); n->rt_store32 = !(e && atoi(e) == 0); }      // 32-byte epilogue stores (aec_rt.cuh)
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
     int chunk0 = 0, nc = 0;
     n->sweep_win_chunks = 0;

@@ -76,6 +76,7 @@ constexpr int kItemTileBytes = 128 * 128;      // one item's hi (or lo) rows: 12
 constexpr int kSiteTileBytes = 2 * kItemTileBytes;   // hi (or lo) tile of a site stage: 256 rows
 constexpr int kSiteStageBytes = 2 * kSiteTileBytes;  // hi + lo
 constexpr int kSiteStages = 2;
+constexpr int kMaxSiteStages = 4;              // half-unit mode: every item slot of the two stages is a stage of its own
 constexpr int kMaxWStages = 4;
 constexpr int kMaxMtu = 2;                     // weight tiles per unit (2 x 256 accumulator columns)
 constexpr int kSiteRing = 4;                   // site-info buffers: producers may run this many units ahead of the epilogue
@@ -229,6 +230,7 @@ struct TcParams {
     int pW, pWw, pHWw;
     float pool_alpha;           // this layer's activation slope (the pool ranks rates R = A * slope(F))
     unsigned long long *timing; // null, or 16 cycle counters accumulated over CTAs (aec_net_tc_timing): see TcTimingSlot
+    int half_units;             // weights-as-M: 0 never, 1 = units of 64 sites (N = 128) when full units would leave CTAs idle (few streams)
     int debug;                  // AEC_TC_DEBUG experiment bits (results invalid when non-zero): 1 no gather loads, 2 no operand stores, 4 no MMA, 8 no epilogue stores, 16 no weight copies
 };
 
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
 {
     static_assert(!kPool || (kFastDecode && !kSM), "the fused pool lives in the weights-as-M epilogue and the batched decoder");
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ __align__(8) uint64_t bar_x_full[kSiteStages], bar_x_empty[kSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
+    __shared__ __align__(8) uint64_t bar_x_full[kMaxSiteStages], bar_x_empty[kMaxSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[kSiteRing], bar_si_free[kSiteRing];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) SiteSrc s_src[kSiteRing][kUnitSites];
@@ -365,8 +367,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_sites = __shfl_sync(0xffffffffu, *p.counter, 0);      // warp-uniform for the compiler's sake
     if (blockIdx.x == 0 && tid == 0 && n_sites > 0) atomicAdd(p.accum, (unsigned long long)(kPool ? *p.site_counter : n_sites));
-    const int n_blocks = (n_sites + kUnitSites - 1) / kUnitSites;
     const int n_mgroups = (p.m_tiles + p.mtu - 1) / p.mtu;
+    // Few sites (few streams, deep layers): with 128-site units fewer units than CTAs - then a unit is ONE 64-site item (MMA
+    // N = 128, half the tensor time per K block, twice the CTAs at work); the layout of an item inside stage and accumulator
+    // is unchanged.  Uniform over the grid: every CTA reads the same counter.
+    const bool half = !kSM && p.half_units && ((n_sites + kUnitSites - 1) / kUnitSites) * n_mgroups < (int)gridDim.x;
+    const int usites = half ? kItemSites : kUnitSites;          // sites per unit
+    const int ipk = half ? 1 : 2;                               // items per K block
+    // Site stages: two of two items each, or - half units - the same four item slots as four one-item stages.  Three producer
+    // groups take the items round-robin, so a group's consecutive items are three apart: with fewer than three stages it
+    // could reach a stage TWO uses ahead of its consumer, and a parity wait cannot tell "two phases behind" from "done".
+    const uint32_t n_xst = half ? (uint32_t)kMaxSiteStages : (uint32_t)kSiteStages;
+    // first byte of site stage sx (its hi tile; the lo tile is kSiteTileBytes behind): item slot (sx >> 1, sx & 1) when a stage is one item
+    auto stage_off = [&](uint32_t sx) { return half ? (sx >> 1) * (uint32_t)kSiteStageBytes + (sx & 1u) * (uint32_t)kItemTileBytes : sx * (uint32_t)kSiteStageBytes; };
+    const int n_blocks = (n_sites + usites - 1) / usites;
     const int total_units = n_blocks * n_mgroups;
     if ((int)blockIdx.x >= total_units) return;       // uniform per CTA: nothing allocated yet
 
@@ -375,8 +389,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     unsigned char *smem_x = smem_w + (size_t)p.w_stages * 2 * w_tile;
 
     if (tid == 0) {
-        for (int i = 0; i < kSiteStages; ++i) {
-            mbar_init(smem_u32(&bar_x_full[i]), 2 * kGroupThreads);      // both halves of the stage (two producer groups)
+        for (int i = 0; i < (int)n_xst; ++i) {
+            mbar_init(smem_u32(&bar_x_full[i]), (uint32_t)(ipk * kGroupThreads));   // every item of the stage (one producer group each)
             mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
         for (int i = 0; i < p.w_stages; ++i) {
@@ -548,12 +562,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     };
                     issue(0, va, ra);
 #pragma unroll 1
-                    for (int g8 = 0; g8 < kUnitSites / 8; g8 += 2) {
+                    for (int g8 = 0; g8 < usites / 8; g8 += 2) {
                         tmem_ld_wait();
                         issue(g8 + 1, vb, rb);
                         emit(g8, va, ra);
                         tmem_ld_wait();
-                        if (g8 + 2 < kUnitSites / 8) issue(g8 + 2, va, ra);
+                        if (g8 + 2 < usites / 8) issue(g8 + 2, va, ra);
                         emit(g8 + 1, vb, rb);
                     }
                 }
@@ -586,14 +600,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     };
                     const int cstep = 16 * p.rep;                         // this copy's chunks: cc = 16g, 16g + cstep, ...
                     tmem_ld16(taddr + (uint32_t)(16 * g), ra);
+                    const int ncols = 2 * usites;                         // a half unit fills the first item's 128 columns only
 #pragma unroll 1
-                    for (int cc = 16 * g; cc < kUnitCols; cc += 2 * cstep) {
+                    for (int cc = 16 * g; cc < ncols; cc += 2 * cstep) {
                         tmem_ld_wait();
-                        if (cc + cstep < kUnitCols) tmem_ld16(taddr + (uint32_t)(cc + cstep), rb);
+                        if (cc + cstep < ncols) tmem_ld16(taddr + (uint32_t)(cc + cstep), rb);
                         store16(ra, cc);
-                        if (cc + cstep >= kUnitCols) break;
+                        if (cc + cstep >= ncols) break;
                         tmem_ld_wait();
-                        if (cc + 2 * cstep < kUnitCols) tmem_ld16(taddr + (uint32_t)(cc + 2 * cstep), ra);
+                        if (cc + 2 * cstep < ncols) tmem_ld16(taddr + (uint32_t)(cc + 2 * cstep), ra);
                         store16(rb, cc + cstep);
                     }
                 }
@@ -620,7 +635,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         // measured (tools/bench_umma.cu), every mbarrier.try_wait in the issuing warp costs ~170 cycles
         // that the tensor pipe idles (the wait queues behind the in-flight MMAs), so all operand waits
         // live in the gatekeeper warp, which releases each pass through a named barrier (ids 1..4).
-        const uint32_t idesc = make_idesc_tf32(kUnitCols);
+        const uint32_t idesc = make_idesc_tf32(half ? kUnitCols / 2 : kUnitCols);
         const uint32_t idesc_cat = make_idesc_tf32(kSM ? 2 * p.Mrows : kUnitCols), idesc_hi = make_idesc_tf32(kSM ? p.Mrows : kUnitCols);
         const uint32_t x_base = smem_u32(smem_x), w_base = smem_u32(smem_w);
         uint32_t qx = 0, qw = 0;
@@ -632,8 +647,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
             const int ab = ul % p.n_acc;
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
-                const uint32_t sx = qx % (uint32_t)kSiteStages;
-                const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes, x_lo = x_hi + (uint32_t)kSiteTileBytes;
+                const uint32_t sx = qx % n_xst;
+                const uint32_t x_hi = x_base + stage_off(sx), x_lo = x_hi + (uint32_t)kSiteTileBytes;
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
                     const uint32_t w_hi = w_base + sw * 2u * w_tile, w_lo = w_hi + w_tile;
@@ -704,8 +719,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const uint32_t ua = (uint32_t)(ul / p.n_acc);
             if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
-                const uint32_t sx = qx % (uint32_t)kSiteStages;
-                const uint32_t px = (qx / (uint32_t)kSiteStages) & 1u;
+                const uint32_t sx = qx % n_xst;
+                const uint32_t px = (qx / n_xst) & 1u;
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
                     // every wait costs ~170 cycles even when the barrier is already complete: the weights (normally early)
@@ -766,8 +781,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 uint32_t ent[kUnitSites / 32];
     #pragma unroll
                 for (int k = 0; k < kUnitSites / 32; ++k) {
-                    const long long gi = (long long)blk * kUnitSites + lane + 32 * k;
-                    ent[k] = gi < n_sites ? __ldg(p.sites + gi) : 0xffffffffu;
+                    const long long gi = (long long)blk * usites + lane + 32 * k;
+                    ent[k] = (lane + 32 * k < usites && gi < n_sites) ? __ldg(p.sites + gi) : 0xffffffffu;
                 }
                 if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
     #pragma unroll
@@ -804,11 +819,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             } else {
                 if (us > 0) mbar_wait(smem_u32(&bar_si_free[buf]), (us - 1) & 1u);
                 for (int i = lane; i < kUnitSites; i += 32) {
-                    const long long gi = (long long)blk * kUnitSites + i;
+                    const long long gi = (long long)blk * usites + i;
                     SiteSrc q;
                     q.ptr = p.zero_f; q.taps = 0u; q.pad = 0u;
                     long long dst = -1;
-                    if (gi < n_sites) {
+                    if (i < usites && gi < n_sites) {
                         int s, y, x;
                         site_decode(p.code, p.sites[gi], s, y, x);
                         const int site = y * p.W + x;
@@ -836,13 +851,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         const int g = pt / kGroupThreads, t = pt - g * kGroupThreads;
         long long tw_si = 0, tw_x = 0;
         const long long t_begin = timing ? clock64() : 0;
-        const uint32_t q_end = (uint32_t)n_units_cta * (uint32_t)p.KB * 2u;
+        const uint32_t q_end = (uint32_t)n_units_cta * (uint32_t)p.KB * (uint32_t)ipk;      // items: ipk per (unit, K block)
         struct Pos { int ul, kb, h; uint32_t q; };
         auto advance = [&](Pos &c) {
             c.q += kGroups;
             c.h += kGroups;
-            c.kb += c.h >> 1;
-            c.h &= 1;
+            if (ipk == 2) { c.kb += c.h >> 1; c.h &= 1; } else { c.kb += c.h; c.h = 0; }
             while (c.kb >= p.KB) { c.kb -= p.KB; ++c.ul; }
         };
         int ready_ul = -1;                 // units whose site info this thread has already waited for
@@ -857,20 +871,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         };
         const uint32_t x_base = smem_u32(smem_x);
         auto store = [&](const Pos &c, const float4 (&f)[kPairs], const float4 (&a)[kPairs]) {
-            const uint32_t qx = c.q >> 1;
-            const uint32_t sx = qx % (uint32_t)kSiteStages, use = qx / (uint32_t)kSiteStages;
+            const uint32_t qx = ipk == 2 ? c.q >> 1 : c.q;
+            const uint32_t sx = qx % n_xst, use = qx / n_xst;
             if (use > 0) timed_wait(smem_u32(&bar_x_empty[sx]), (use - 1) & 1u, timing, tw_x);   // MMAs that read this stage are done
             // weights-as-M: an item's 128 rows (64 value rows, then its 64 rate rows) are one half of the 256-row tile;
             // sites-as-M: its value rows are rows 64h.. of tile_v and its rate rows the same rows of tile_r (16 KB behind)
             constexpr uint32_t kHalfStride = kSM ? (uint32_t)(kItemSites / 8) * 1024u : (uint32_t)kItemTileBytes;
             constexpr uint32_t kRateOff = kSM ? (uint32_t)kItemTileBytes : (uint32_t)(kItemSites / 8) * 1024u;
-            const uint32_t x_hi = x_base + sx * (uint32_t)kSiteStageBytes + (uint32_t)c.h * kHalfStride;
+            const uint32_t x_hi = x_base + stage_off(sx) + (uint32_t)c.h * kHalfStride;          // c.h == 0 when a stage is one item
             item_store<kRateOff>(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
             fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
             mbar_arrive(smem_u32(&bar_x_full[sx]));
         };
         Pos cur;
-        cur.q = (uint32_t)g; cur.ul = 0; cur.kb = g >> 1; cur.h = g & 1;
+        cur.q = (uint32_t)g; cur.ul = 0; cur.kb = ipk == 2 ? g >> 1 : g; cur.h = ipk == 2 ? g & 1 : 0;
         while (cur.kb >= p.KB) { cur.kb -= p.KB; ++cur.ul; }
         float4 fa[kPairs], aa[kPairs], fb[kPairs], ab4[kPairs];
         if (cur.q < q_end) {

@@ -518,3 +518,30 @@ def test_pool_in_conv_epilogue_changes_no_bit(monkeypatch):
         assert nets[0].unit_counters()[names.index(nm)] > 0 and nets[1].unit_counters()[names.index(nm)] == 0
     for n in nets:
         n.close()
+
+
+def test_half_units_change_no_bit(monkeypatch):
+    """With few sites on a layer's work list the gathered kernel cuts units of 64 sites (one MMA of N = 128 per product)
+    instead of 128, so that more CTAs work on a small job.  Same accumulation order per site: AEC_TC_HALF=0 (always 128-site
+    units) must give bit-identical heads, maps, pool state and frontiers - which also runs this small net through the
+    full-unit path that otherwise only many-stream workloads take."""
+    S, steps, h, w = 3, 40, 32, 48
+    wts = P.xavier_weights(POOL_IN_CONV, seed=6)
+    evs = P.synthetic_events("uniform", S, steps, 30, h, w, seed=10)
+    nets = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AEC_TC_HALF", flag)
+        nets.append(EventNetCuda(h, w, POOL_IN_CONV, wts, 5e-5, 0.1, "SAME", n_streams=S))
+    for t in range(steps):
+        per = [evs[s, t] for s in range(S)]
+        ha, hb = nets[0].step(per), nets[1].step(per)
+        assert np.array_equal(ha, hb), "step %d head" % t
+        if t % 8 == 7 or t == steps - 1:
+            for s in range(S):
+                for i in range(len(nets[0].names)):
+                    sa, sb = nets[0].state(i, s), nets[1].state(i, s)
+                    for key in sa:
+                        assert np.array_equal(sa[key], sb[key]), "step %d stream %d layer %s %s" % (t, s, nets[0].names[i], key)
+                    assert np.array_equal(nets[0].frontier(i, s), nets[1].frontier(i, s))
+    for n in nets:
+        n.close()

@@ -7,6 +7,7 @@
 //   mode 4  st.global.v2.b32, 4 lanes = one 32-byte sector of a row, 8 rows per instruction (the tcgen05.ld.16x256b register layout)
 //   mode 5  st.global.v4.b32, 2 lanes = one 32-byte sector of a row, 16 rows per instruction
 //   mode 6  st.global.v8.f32 (STG.256), lane = row: 32 full sectors of 32 different rows per instruction
+//   mode 7  mode 0 with eight independent rows per loop iteration
 // All 148 CTAs write disjoint regions of a 1 GB buffer; rows are visited in a hashed order.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bench_store.bin tools/bench_store.cu
 #include <cstdio>
@@ -52,6 +53,17 @@ __global__ void __launch_bounds__(1024, 1) k_store(char *buf, long long region, 
             char *d2 = base + (size_t)((row + (uint32_t)lane) & row_mask) * (uint32_t)row_bytes;
             for (int c = 0; c < row_bytes; c += 32) asm volatile("st.global.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(d2 + c), "f"(v) : "memory");
             r += 31;
+        } else if (mode == 7) {
+            // mode 0 with EIGHT independent rows per loop iteration (does a warp's rate depend on how many stores it has in flight?)
+            uint32_t rows8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rows8[k] = ((h >> 8) + 0x9e37u * (uint32_t)(k + 1) * 977u) & row_mask;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                char *d2 = base + (size_t)rows8[k] * (uint32_t)row_bytes;
+                for (int c = lane * 4; c < row_bytes; c += 128) *reinterpret_cast<float *>(d2 + c) = v;
+            }
+            r += 7;
         } else if (mode == 2) {
             for (int c = lane * 16; c < row_bytes; c += 512) *reinterpret_cast<float4 *>(dst + c) = make_float4(v, v, v, v);
         } else {
@@ -76,10 +88,10 @@ int main()
     cudaMalloc(&buf, 148 * region);
     cudaMalloc(&out, 148 * sizeof(long long));
     cudaFuncSetAttribute(k_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
-    const char *names[7] = {"st.b32 lane=channel (128 B runs)", "st.v4 lane=row (32 rows/instr)", "st.v4 8+ lanes per row (512 B/instr)", "cp.async.bulk per row",
-                            "st.v2 4 lanes = 32 B (8 rows/instr)", "st.v4 2 lanes = 32 B (16 rows/instr)", "st.v8 lane=row (32 rows x 32 B/instr)"};
+    const char *names[8] = {"st.b32 lane=channel (128 B runs)", "st.v4 lane=row (32 rows/instr)", "st.v4 8+ lanes per row (512 B/instr)", "cp.async.bulk per row",
+                            "st.v2 4 lanes = 32 B (8 rows/instr)", "st.v4 2 lanes = 32 B (16 rows/instr)", "st.v8 lane=row (32 rows x 32 B/instr)", "st.b32 lane=channel, 8 rows per iteration"};
     for (int row_bytes : {128, 256, 512})
-        for (int mode = 0; mode < 7; ++mode)
+        for (int mode = 0; mode < 8; ++mode)
             for (int warps : {4, 8, 16}) {
                 const int rows_per_warp = 8192 * 4 / warps;
                 for (int rep = 0; rep < 2; ++rep) {
