@@ -567,7 +567,7 @@ __device__ __forceinline__ void pool_next(PoolBest &b, int row, float f, float a
 //           exactly like the plain sweep (same arithmetic, sign flips into signchg), and a sticky window none of whose sites
 //           is re-evaluated gets its argmax / (Fp, Ap) copy / unstable bit from those registers (cutils.pyx:161-177).
 // Its own kernel (grid: chunks x S) so that the plain sweep keeps its 48 registers per thread.
-__global__ void __launch_bounds__(kThreads) k_sweep_windows(const __grid_constant__ SweepWindowsParams p)
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_windows(const __grid_constant__ SweepWindowsParams p)
 {
     __shared__ int s_win[kSweepMaxWords * 32];
     __shared__ int s_scan[9];
