@@ -193,35 +193,75 @@ def workload_config(args, streams):
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (a query takes well under a millisecond,
+    so even a 70 ms region gets samples), `nvidia-smi -lms` as the fallback (its first line can take longer than the region:
+    start() then waits for it)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]          # NVML clocks event reasons: HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag, self.source = [], None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._sample_nvml()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+            self.rows = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t_end = time.perf_counter() + 3.0
+            while not self.rows and time.perf_counter() < t_end:      # the first line can take a second on a busy host
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def _sample_nvml(self):
+        sm = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+        mask = int(self._reasons(self.handle))
+        self.rows.append((time.perf_counter(), [str(sm), str(self.max_mhz), ""] + ["Active" if mask & b else "Not Active" for b in self.BITS]))
+
+    def _loop_nvml(self):
+        while not self.stop_flag:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        if not self.proc and not self.nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"], "samples": 0}
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for t, r in self.rows if t0 - 0.2 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
         sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(rows)}
+                "samples": len(rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
