@@ -1633,6 +1633,16 @@ __global__ void __launch_bounds__(kThreads) k_head(HeadParams p)
 {
     const long long per = (long long)p.src.H * p.src.W * p.src.C;
     const long long total = per * p.S;
+    if (p.src.kind == 1 && (per & 1) == 0) {
+        // a conv / pool map is channel-last like the head: element i of stream s is F[s * fstride + i]; two per thread
+        const long long per2 = per >> 1, total2 = per2 * p.S;
+        for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total2; i += (long long)gridDim.x * kThreads) {
+            const long long s = i / per2, r2 = i - s * per2;
+            const float2 f = __ldg(reinterpret_cast<const float2 *>(p.src.F + s * p.src.fstride) + r2);
+            reinterpret_cast<float2 *>(p.out + s * per)[r2] = make_float2(__fmul_rn(f.x, slope_of(f.x, p.src.alpha)), __fmul_rn(f.y, slope_of(f.y, p.src.alpha)));
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         const int s = (int)(i / per);
         const long long rem = i - (long long)s * per;
