@@ -65,6 +65,7 @@ struct HostLayer {
     bool pool_in_conv = false;     // pool: ... by the conv layer in front of it
     bool tc_fast_decode = false;   // which site-decoder variant of k_conv_eval_tc the layer runs (fixed at finalize)
     bool tc_sm = false;            // sites-as-M form of the kernel (Cout <= 64, multiple of 4): aec_tc.cuh
+    bool tc_pair = false;          // CTA pairs (tcgen05 cta_group::2, M = 256): an even number of weight tiles and many streams (finalize)
     // row-tile form (aec_rt.cuh) of a sites-as-M layer: units of rt_R output rows x one x segment instead of single sites
     bool rt = false;
     int rt_R = 0, rt_sw_shift = 0, rt_SEG = 0, rt_nxg = 0, rt_CB = 0, rt_ncb = 0, rt_P = 0, rt_xst = 0, rt_wst = 0;
@@ -97,6 +98,7 @@ struct aec_net {
     uint32_t *sites = nullptr;
     bool sweep_skip = true;              // the leak sweep leaves the sites alone that the step re-evaluates (AEC_SWEEP_SKIP=0: leak every live site)
     bool tc_half = true, rt_store32 = true;   // developer switches read at finalize (AEC_TC_HALF, AEC_RT_STORE32)
+    int tc_pair_mode = -1;                    // AEC_TC_PAIR: 0 never, 1 wherever the layer allows it, unset (-1): from 32 streams on
     FrontLayer *front_table = nullptr;   // device copy of the per-layer frontier descriptors (k_frontier_all)
     int front_max_words = 0;
     int *counts = nullptr, *err_flag = nullptr;
@@ -590,6 +592,20 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
     return launch_check(n, "k_leak_sweep");
 }
 
+// CTA-pair form: clusters of two CTAs (one TPC), launched through the extensible API (captured into the step graph like any launch)
+static int launch_tc_pair(void (*fn)(const tc::TcParams), const HostLayer &l, cudaStream_t st, const tc::TcParams &p)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)l.tc_blocks); cfg.blockDim = dim3(tc::kTcThreads); cfg.dynamicSmemBytes = l.tc_smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, fn, p));
+    return AEC_OK;
+}
+
 static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step)
 {
     HostLayer &l = n->L[li];
@@ -617,9 +633,11 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step
         p.quad_bit = 0x80000000u; p.site_counter = n->counts + 32 + li;
         p.pool_idx = pl.idx; p.pool_Fp = pl.Fp; p.pool_Ap = pl.Ap; p.pool_stride = pl.fstride; p.pool_flags = pl.flags;
         p.pool_accum = n->accum + (li + 1); p.pW = pl.W; p.pWw = pl.Ww; p.pHWw = pl.H * pl.Ww; p.pool_alpha = l.alpha;
-        tc::k_conv_eval_tc<true, false, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+        if (l.tc_pair) { if (int rc = launch_tc_pair(tc::k_conv_eval_tc<true, false, true, true>, l, st, p)) return rc; }
+        else tc::k_conv_eval_tc<true, false, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     } else
-    if (l.tc_sm) tc::k_conv_eval_tc<true, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    if (l.tc_pair) { if (int rc = launch_tc_pair(tc::k_conv_eval_tc<true, false, false, true>, l, st, p)) return rc; }
+    else if (l.tc_sm) tc::k_conv_eval_tc<true, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else if (l.tc_fast_decode) tc::k_conv_eval_tc<true, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     else tc::k_conv_eval_tc<false, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
     int rc = launch_check(n, "k_conv_eval_tc");
@@ -949,6 +967,7 @@ extern "C" int aec_net_finalize(aec_net *n)
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
     { const char *e = getenv("AEC_TC_DEBUG"); n->tc_debug = e ? atoi(e) : 0; }
     { const char *e = getenv("AEC_TC_HALF"); n->tc_half = !(e && atoi(e) == 0); }            // 64-site units for small work lists (aec_tc.cuh)
+    { const char *e = getenv("AEC_TC_PAIR"); n->tc_pair_mode = e ? (atoi(e) != 0) : -1; }      // CTA pairs for layers with 2, 4, ... weight tiles
     { const char *e = getenv("AEC_RT_STORE32"); n->rt_store32 = !(e && atoi(e) == 0); }      // 32-byte epilogue stores (aec_rt.cuh)
     memset(&n->sweep_all, 0, sizeof n->sweep_all);
     int chunk0 = 0, nc = 0;
@@ -1006,11 +1025,25 @@ extern "C" int aec_net_finalize(aec_net *n)
                 // weight tiles; the environment is read here, once, not at every launch
                 const char *fk = getenv("AEC_TC_FASTDEC_KB");
                 l.tc_fast_decode = l.KB >= (fk ? atoi(fk) : 10) || (l.m_tiles > 1 && !fk) || l.pool_fuse;
+                // Two CTAs per unit (aec_tc.cuh, kPair) where the layer has an even number of weight tiles.  With few streams the
+                // work lists are short and 64-site units on single CTAs spread them over more SMs: pairs from 32 streams on.
+                l.tc_pair = !l.tc_sm && l.m_tiles % 2 == 0 && l.mtu == 1 && n->num_sms >= 2 &&
+                            (n->tc_pair_mode == 1 || (n->tc_pair_mode < 0 && n->S >= 32));
+                if (l.tc_pair) {
+                    l.tc_fast_decode = true;
+                    l.tc_blocks = n->num_sms & ~1;
+                    // a CTA of a pair converts half of a unit's sites: three 32 KB site stages, the rest goes to the weight ring
+                    const size_t w_stage = 2 * (size_t)l.Mrows * 128, x_bytes = (size_t)tc::kPairSiteStages * 2 * tc::kItemTileBytes;
+                    l.w_stages = (int)std::min<size_t>(tc::kMaxWStages, std::max<size_t>(2, (210 * 1024 - x_bytes) / w_stage));
+                    l.tc_smem = x_bytes + (size_t)l.w_stages * w_stage + 1024;
+                    tc_max = std::max(tc_max, l.tc_smem);
+                }
             }
         if (tc_max > 227 * 1024) return fail(AEC_EINVAL, "tensor-core conv tile needs %zu bytes of shared memory", tc_max);
         if (tc_max) {
-            const void *variants[4] = {(const void *)tc::k_conv_eval_tc<false, false>, (const void *)tc::k_conv_eval_tc<true, false>,
-                                       (const void *)tc::k_conv_eval_tc<true, true>, (const void *)tc::k_conv_eval_tc<true, false, true>};
+            const void *variants[6] = {(const void *)tc::k_conv_eval_tc<false, false>, (const void *)tc::k_conv_eval_tc<true, false>,
+                                       (const void *)tc::k_conv_eval_tc<true, true>, (const void *)tc::k_conv_eval_tc<true, false, true>,
+                                       (const void *)tc::k_conv_eval_tc<true, false, false, true>, (const void *)tc::k_conv_eval_tc<true, false, true, true>};
             for (const void *fn : variants) {
                 cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max);
                 if (e != cudaSuccess) return fail(AEC_ECUDA, "cannot opt in to %zu bytes of dynamic shared memory for the tensor-core conv kernel: %s", tc_max, cudaGetErrorString(e));

@@ -77,6 +77,7 @@ constexpr int kSiteTileBytes = 2 * kItemTileBytes;   // hi (or lo) tile of a sit
 constexpr int kSiteStageBytes = 2 * kSiteTileBytes;  // hi + lo
 constexpr int kSiteStages = 2;
 constexpr int kMaxSiteStages = 4;              // half-unit mode: every item slot of the two stages is a stage of its own
+constexpr int kPairSiteStages = 3;             // CTA pairs: three one-item stages of 32 KB (hi, lo), the rest of the shared memory holds weight stages
 constexpr int kMaxWStages = 4;
 constexpr int kMaxMtu = 2;                     // weight tiles per unit (2 x 256 accumulator columns)
 constexpr int kSiteRing = 4;                   // site-info buffers: producers may run this many units ahead of the epilogue
@@ -141,9 +142,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr)
 }
 
 // Instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n, int m = 128)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
@@ -182,6 +183,58 @@ __device__ __forceinline__ bool elect_one()
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
     return pred != 0;
+}
+// ---- CTA pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank)
+        : "memory");
+}
+// wait (bounded) that also acquires what a thread of the other CTA released before its remote arrive
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+// D (M = 256: rows 0-127 in this CTA's TMEM, 128-255 in the peer's) += A (128 rows from each CTA's shared memory) x B (N/2 rows from each)
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of the pair's MMAs -> the mbarrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -348,13 +401,24 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
 // The weight stages come first: the A descriptor always spans 128 rows, so with Mrows < 128 it reads
 // past the tile into whatever follows (the next stage / the site stages); those rows only feed
 // accumulator lanes >= Mrows, which the epilogue never reads.
-template <bool kFastDecode, bool kSM, bool kPool = false>
+//
+// kPair (weights-as-M, an even number of weight tiles): two CTAs of a cluster (one TPC) work on a unit together with
+// tcgen05.mma.cta_group::2, M = 256: CTA r of the pair holds weight tile 2*pg + r (the A rows 128r ..) and the accumulator of
+// those channels, and converts only item r (64 of the unit's 128 sites, half of the B rows); the tensor cores read the
+// other half from the peer's shared memory.  Per K block and SM: 32 KB of operand stores instead of 64 and 8 KB instead of
+// 12 KB of operand reads per MMA - the shared-memory path is what bounds the one-CTA form (header).  Only the leader
+// (rank 0) issues MMAs; the peer's gatekeeper relays "my stage, my weights and my accumulator are ready" to a ring of
+// mbarriers in the leader, and every commit is multicast to the barriers of both CTAs.  Column c of the accumulator
+// sees the same instruction sequence as in the one-CTA form: results are bit-identical (test_pair_units_change_no_bit).
+template <bool kFastDecode, bool kSM, bool kPool = false, bool kPair = false>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
     static_assert(!kPool || (kFastDecode && !kSM), "the fused pool lives in the weights-as-M epilogue and the batched decoder");
+    static_assert(!kPair || (kFastDecode && !kSM), "CTA pairs: weights-as-M form with the batched decoder");
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ __align__(8) uint64_t bar_x_full[kMaxSiteStages], bar_x_empty[kMaxSiteStages], bar_w_full[kMaxWStages], bar_w_empty[kMaxWStages];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_si_full[kSiteRing], bar_si_free[kSiteRing];
+    __shared__ __align__(8) uint64_t bar_peer[4];      // kPair, leader: the peer's gatekeeper arrives for pass qw on [qw & 3]
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) SiteSrc s_src[kSiteRing][kUnitSites];
     __shared__ __align__(16) long long s_dst[kSiteRing][kUnitSites];   // byte offset of the site's channel 0 in F (and in A)
@@ -367,22 +431,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_sites = __shfl_sync(0xffffffffu, *p.counter, 0);      // warp-uniform for the compiler's sake
     if (blockIdx.x == 0 && tid == 0 && n_sites > 0) atomicAdd(p.accum, (unsigned long long)(kPool ? *p.site_counter : n_sites));
-    const int n_mgroups = (p.m_tiles + p.mtu - 1) / p.mtu;
+    const uint32_t crank = kPair ? cluster_ctarank() : 0u;                    // 0 = leader of the pair
+    const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // CTA (or pair) index ...
+    const int n_workers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;     // ... of this many
+    const int n_mgroups = kPair ? p.m_tiles / 2 : (p.m_tiles + p.mtu - 1) / p.mtu;
     // Few sites (few streams, deep layers): with 128-site units fewer units than CTAs - then a unit is ONE 64-site item (MMA
     // N = 128, half the tensor time per K block, twice the CTAs at work); the layout of an item inside stage and accumulator
     // is unchanged.  Uniform over the grid: every CTA reads the same counter.
-    const bool half = !kSM && p.half_units && ((n_sites + kUnitSites - 1) / kUnitSites) * n_mgroups < (int)gridDim.x;
+    const bool half = !kSM && !kPair && p.half_units && ((n_sites + kUnitSites - 1) / kUnitSites) * n_mgroups < (int)gridDim.x;
     const int usites = half ? kItemSites : kUnitSites;          // sites per unit
-    const int ipk = half ? 1 : 2;                               // items per K block
+    const bool one_item = half || kPair;                        // a site stage of this CTA is ONE item (pair: the CTA's half of the unit)
+    const int ipk = one_item ? 1 : 2;                           // items per K block (converted by this CTA)
     // Site stages: two of two items each, or - half units - the same four item slots as four one-item stages.  Three producer
     // groups take the items round-robin, so a group's consecutive items are three apart: with fewer than three stages it
     // could reach a stage TWO uses ahead of its consumer, and a parity wait cannot tell "two phases behind" from "done".
-    const uint32_t n_xst = half ? (uint32_t)kMaxSiteStages : (uint32_t)kSiteStages;
+    const uint32_t n_xst = kPair ? (uint32_t)kPairSiteStages : one_item ? (uint32_t)kMaxSiteStages : (uint32_t)kSiteStages;
     // first byte of site stage sx (its hi tile; the lo tile is kSiteTileBytes behind): item slot (sx >> 1, sx & 1) when a stage is one item
-    auto stage_off = [&](uint32_t sx) { return half ? (sx >> 1) * (uint32_t)kSiteStageBytes + (sx & 1u) * (uint32_t)kItemTileBytes : sx * (uint32_t)kSiteStageBytes; };
+    constexpr uint32_t kLoOff = kPair ? (uint32_t)kItemTileBytes : (uint32_t)kSiteTileBytes;      // from a stage's hi tile to its lo tile
+    auto stage_off = [&](uint32_t sx) { return kPair ? sx * 2u * (uint32_t)kItemTileBytes : one_item ? (sx >> 1) * (uint32_t)kSiteStageBytes + (sx & 1u) * (uint32_t)kItemTileBytes : sx * (uint32_t)kSiteStageBytes; };
     const int n_blocks = (n_sites + usites - 1) / usites;
     const int total_units = n_blocks * n_mgroups;
-    if ((int)blockIdx.x >= total_units) return;       // uniform per CTA: nothing allocated yet
+    if (worker >= total_units) return;                // uniform per CTA (and per pair): nothing allocated yet
 
     unsigned char *smem_w = reinterpret_cast<unsigned char *>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t w_tile = (uint32_t)p.Mrows * 128u;             // one weight tile (hi or lo)
@@ -405,19 +474,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             mbar_init(smem_u32(&bar_si_full[i]), 1);
             mbar_init(smem_u32(&bar_si_free[i]), kEpiWarps * 32);
         }
+        if constexpr (kPair)
+            for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar_peer[i]), 1);
         fence_barrier_init();
     }
     for (int i = tid; i < min(p.KB, kKtabBlocks) * 8; i += kTcThreads) s_ktab[i] = make_kentry(p, i >> 3, i & 7);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (kPair) {      // the same warp of both CTAs
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();      // both CTAs' barriers initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
     const bool timing = p.timing != nullptr;
-    const int n_units_cta = (total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_units_cta = (total_units - worker + n_workers - 1) / n_workers;
+    // weight tiles of unit (.., mg) that THIS CTA holds: first tile and how many
+    auto tile0_of = [&](int mg) { return kPair ? 2 * mg + (int)crank : mg * p.mtu; };
+    auto tiles_of = [&](int mg) { return kPair ? 1 : min(p.mtu, p.m_tiles - mg * p.mtu); };
 
     if (warp < kEpiWarps) {
         // ===================== epilogue =====================
@@ -430,9 +510,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         int n_quads = 0;                                     // kPool: windows evaluated here (counted once, by the first weight tile's CTA)
         const long long t_begin = timing ? clock64() : 0;
         for (int ul = 0; ul < n_units_cta; ++ul) {
-            const int unit = blockIdx.x + ul * gridDim.x;
+            const int unit = worker + ul * n_workers;
             const int mg = unit % n_mgroups;
-            const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+            const int mt_count = tiles_of(mg);
             const int buf = ul % kSiteRing, ab = ul % p.n_acc;
             timed_wait(smem_u32(&bar_si_full[buf]), (uint32_t)(ul / kSiteRing) & 1u, timing, tw_si);
             timed_wait(smem_u32(&bar_acc_full[ab]), (uint32_t)(ul / p.n_acc) & 1u, timing, tw_acc);
@@ -490,7 +570,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 // columns and the rate columns 64 further on - so that a quad's four (F, A) pairs are in registers together.
                 // The list may hold padding entries anywhere (end of a stream's block): every site is checked by its own offset.
                 for (int mt = 0; mt < mt_count; ++mt) {
-                    const int c = (mg * p.mtu + mt) * p.Mch + row;
+                    const int c = (tile0_of(mg) + mt) * p.Mch + row;
                     const bool c_ok = row < p.Mrows && c < p.C && !(p.debug & 8);
                     const long long a_minus_f = (const char *)p.A - (const char *)p.F;
                     const float bias = c_ok ? __ldg(p.bias + c) : 0.f;
@@ -557,7 +637,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                                 const uint32_t code = s_pflag[buf][(i0 >> 2) + q];
                                 atomicOr(p.pool_flags + (code >> 5), 1u << (code & 31u));
                             }
-                            if (pw[q] >= 0 && mt == 0 && mg * p.mtu == 0 && warp == 0 && lane == 0) ++n_quads;
+                            if (pw[q] >= 0 && tile0_of(mg) + mt == 0 && warp == 0 && lane == 0) ++n_quads;
                         }
                     };
                     issue(0, va, ra);
@@ -576,7 +656,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             if (warp_live) {
                 for (int mt = 0; mt < mt_count; ++mt) {
                     const int g = p.rep > 1 ? (warp * 32) / p.Mch : 0;    // which copy of the channels this warp holds (Mch % 32 == 0 when rep > 1)
-                    const int c = (mg * p.mtu + mt) * p.Mch + (row - g * p.Mch);
+                    const int c = (tile0_of(mg) + mt) * p.Mch + (row - g * p.Mch);
                     const bool c_ok = row < p.Mrows && c < p.C && !(p.debug & 8);
                     const long long a_minus_f = (const char *)p.A - (const char *)p.F;
                     const float bias = c_ok ? __ldg(p.bias + c) : 0.f;
@@ -635,20 +715,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         // measured (tools/bench_umma.cu), every mbarrier.try_wait in the issuing warp costs ~170 cycles
         // that the tensor pipe idles (the wait queues behind the in-flight MMAs), so all operand waits
         // live in the gatekeeper warp, which releases each pass through a named barrier (ids 1..4).
-        const uint32_t idesc = make_idesc_tf32(half ? kUnitCols / 2 : kUnitCols);
+        const uint32_t idesc = kPair ? make_idesc_tf32(kUnitCols, 256) : make_idesc_tf32(half ? kUnitCols / 2 : kUnitCols);
         const uint32_t idesc_cat = make_idesc_tf32(kSM ? 2 * p.Mrows : kUnitCols), idesc_hi = make_idesc_tf32(kSM ? p.Mrows : kUnitCols);
         const uint32_t x_base = smem_u32(smem_x), w_base = smem_u32(smem_w);
         uint32_t qx = 0, qw = 0;
         long long tw_gate = 0;
         const long long t_begin = timing ? clock64() : 0;
-        for (int ul = 0; ul < n_units_cta; ++ul) {
-            const int unit = blockIdx.x + ul * gridDim.x;
+        for (int ul = 0; ul < (kPair && crank != 0 ? 0 : n_units_cta); ++ul) {      // pair: the leader issues for both CTAs
+            const int unit = worker + ul * n_workers;
             const int mg = unit % n_mgroups;
-            const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+            const int mt_count = tiles_of(mg);
             const int ab = ul % p.n_acc;
             for (int kb = 0; kb < p.KB; ++kb, ++qx) {
                 const uint32_t sx = qx % n_xst;
-                const uint32_t x_hi = x_base + stage_off(sx), x_lo = x_hi + (uint32_t)kSiteTileBytes;
+                const uint32_t x_hi = x_base + stage_off(sx), x_lo = x_hi + kLoOff;
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
                     const uint32_t sw = qw % (uint32_t)p.w_stages;
                     const uint32_t w_hi = w_base + sw * 2u * w_tile, w_lo = w_hi + w_tile;
@@ -686,14 +766,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                                 const uint64_t dwh = make_desc_sw128(w_hi + ko), dwl = make_desc_sw128(w_lo + ko);
                                 const uint64_t dxh = make_desc_sw128(x_hi + ko), dxl = make_desc_sw128(x_lo + ko);
                                 if (ks >= ks_n) break;
-                                mma_tf32(d, dwh, dxl, idesc, (kb | ks) != 0 ? 1u : 0u);
-                                mma_tf32(d, dwl, dxh, idesc, 1u);
-                                mma_tf32(d, dwh, dxh, idesc, 1u);
+                                if constexpr (kPair) {
+                                    mma_tf32_pair(d, dwh, dxl, idesc, (kb | ks) != 0 ? 1u : 0u);
+                                    mma_tf32_pair(d, dwl, dxh, idesc, 1u);
+                                    mma_tf32_pair(d, dwh, dxh, idesc, 1u);
+                                } else {
+                                    mma_tf32(d, dwh, dxl, idesc, (kb | ks) != 0 ? 1u : 0u);
+                                    mma_tf32(d, dwl, dxh, idesc, 1u);
+                                    mma_tf32(d, dwh, dxh, idesc, 1u);
+                                }
                             }
                         }
-                        mma_commit(smem_u32(&bar_w_empty[sw]));
-                        if (mt == mt_count - 1) mma_commit(smem_u32(&bar_x_empty[sx]));
-                        if (mt == mt_count - 1 && kb == p.KB - 1) mma_commit(smem_u32(&bar_acc_full[ab]));
+                        if constexpr (kPair) {      // stages and accumulator of BOTH CTAs
+                            mma_commit_pair(smem_u32(&bar_w_empty[sw]));
+                            mma_commit_pair(smem_u32(&bar_x_empty[sx]));
+                            if (kb == p.KB - 1) mma_commit_pair(smem_u32(&bar_acc_full[ab]));
+                        } else {
+                            mma_commit(smem_u32(&bar_w_empty[sw]));
+                            if (mt == mt_count - 1) mma_commit(smem_u32(&bar_x_empty[sx]));
+                            if (mt == mt_count - 1 && kb == p.KB - 1) mma_commit(smem_u32(&bar_acc_full[ab]));
+                        }
                     }
                     __syncwarp();
                 }
@@ -712,9 +804,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         uint32_t qx = 0, qw = 0;
         long long tw_acc = 0, tw_x = 0, tw_w = 0;
         for (int ul = 0; ul < n_units_cta; ++ul) {
-            const int unit = blockIdx.x + ul * gridDim.x;
+            const int unit = worker + ul * n_workers;
             const int mg = unit % n_mgroups;
-            const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+            const int mt_count = tiles_of(mg);
             const int ab = ul % p.n_acc;
             const uint32_t ua = (uint32_t)(ul / p.n_acc);
             if (ua > 0) timed_wait(smem_u32(&bar_acc_empty[ab]), (ua - 1) & 1u, timing, tw_acc);    // epilogue drained this buffer
@@ -727,6 +819,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                     // first, the site stage (normally the last thing to arrive) last, one barrier for both of its halves
                     timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
                     if (mt == 0) timed_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
+                    if constexpr (kPair) {
+                        // The peer relays: everything of pass qw on its side is ready -> bar_peer[qw & 3] of the leader.  It can be
+                        // at most n_xst = 3 passes ahead of the leader's MMAs (its stage of pass qw + 3 is freed by the commit of
+                        // pass qw), so a barrier's previous phase (pass qw - 4) has always been consumed when the next arrival comes.
+                        if (crank != 0) {
+                            if (lane == 0) mbar_arrive_remote(smem_u32(&bar_peer[qw & 3u]), 0u);
+                            __syncwarp();
+                            continue;
+                        }
+                        mbar_wait_cluster(smem_u32(&bar_peer[qw & 3u]), (qw >> 2) & 1u);
+                    }
                     asm volatile("bar.arrive %0, 64;" ::"r"(1u + (qw & 3u)) : "memory");
                 }
             }
@@ -744,15 +847,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             const long long t_begin = timing ? clock64() : 0;
             const size_t tile_floats = (size_t)2 * p.Mrows * kBlockK;        // hi + lo of one (weight tile, K block)
             for (int ul = 0; ul < n_units_cta; ++ul) {
-                const int unit = blockIdx.x + ul * gridDim.x;
+                const int unit = worker + ul * n_workers;
                 const int mg = unit % n_mgroups;
-                const int mt_count = min(p.mtu, p.m_tiles - mg * p.mtu);
+                const int mt_count = tiles_of(mg);
                 for (int kb = 0; kb < p.KB; ++kb) {
                     for (int mt = 0; mt < mt_count; ++mt, ++qw) {
                         const int sw = (int)(qw % (uint32_t)p.w_stages);
                         const uint32_t use = qw / (uint32_t)p.w_stages;
                         if (use > 0) timed_wait(smem_u32(&bar_w_empty[sw]), (use - 1) & 1u, timing, tw_w);
-                        const float *src = p.wimg + ((size_t)(mg * p.mtu + mt) * p.KB + kb) * tile_floats;
+                        const float *src = p.wimg + ((size_t)(tile0_of(mg) + mt) * p.KB + kb) * tile_floats;
                         if (p.debug & 16) { mbar_arrive(smem_u32(&bar_w_full[sw])); continue; }
                         mbar_expect_tx(smem_u32(&bar_w_full[sw]), 2u * w_tile);
                         bulk_g2s(smem_u32(smem_w + (size_t)sw * 2 * w_tile), src, 2u * w_tile, smem_u32(&bar_w_full[sw]));
@@ -769,7 +872,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
         // kFastDecode (layers with long units or several weight tiles): measured 3-4 % faster there, but 2-8 % slower for the short
         // units of the first two tensor-core layers, which keep the simple loop (profiles/r1e_summary.md).
         for (int ul = 0; ul < n_units_cta; ++ul) {
-            const int unit = blockIdx.x + ul * gridDim.x;
+            const int unit = worker + ul * n_workers;
             const int blk = unit / n_mgroups;
             const int buf = ul % kSiteRing;
             const uint32_t us = (uint32_t)(ul / kSiteRing);
@@ -867,7 +970,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 ready_ul = c.ul;
             }
             const KEntry e = c.kb < kKtabBlocks ? s_ktab[c.kb * 8 + (t & 7)] : make_kentry(p, c.kb, t & 7);
-            item_load(p, e, s_src[buf] + c.h * kItemSites, t, f, a);
+            item_load(p, e, s_src[buf] + (kPair ? (int)crank : c.h) * kItemSites, t, f, a);
         };
         const uint32_t x_base = smem_u32(smem_x);
         auto store = [&](const Pos &c, const float4 (&f)[kPairs], const float4 (&a)[kPairs]) {
@@ -879,7 +982,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
             constexpr uint32_t kHalfStride = kSM ? (uint32_t)(kItemSites / 8) * 1024u : (uint32_t)kItemTileBytes;
             constexpr uint32_t kRateOff = kSM ? (uint32_t)kItemTileBytes : (uint32_t)(kItemSites / 8) * 1024u;
             const uint32_t x_hi = x_base + stage_off(sx) + (uint32_t)c.h * kHalfStride;          // c.h == 0 when a stage is one item
-            item_store<kRateOff>(p, x_hi, x_hi + (uint32_t)kSiteTileBytes, t, f, a);
+            item_store<kRateOff>(p, x_hi, x_hi + kLoOff, t, f, a);
             fence_proxy_async();      // generic-proxy writes of X -> visible to the tensor core (async proxy)
             mbar_arrive(smem_u32(&bar_x_full[sx]));
         };
@@ -911,7 +1014,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (kPair) {
+        cluster_sync_all();      // the peer's tensor core reads this CTA's shared memory and writes its TMEM until the last commit
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    } else if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 }  // namespace tc

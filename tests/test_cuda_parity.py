@@ -520,6 +520,65 @@ def test_pool_in_conv_epilogue_changes_no_bit(monkeypatch):
         n.close()
 
 
+PAIR_NET = "conv1=3,3,1,16 pool1=2,2 conv2=3,3,16,96 pool2=2,2 conv3=3,3,96,160 pool3=2,2 conv4=3,3,160,392 conv5=1,1,392,12"
+
+
+def test_pair_units_change_no_bit(monkeypatch):
+    """Layers with an even number of weight tiles run on CTA pairs (tcgen05 cta_group::2, M = 256: each CTA of a cluster
+    holds one weight tile and converts half of the unit's sites, aec_tc.cuh kPair) when there are many streams.  An
+    accumulator column sees the same instruction sequence as on a single CTA: AEC_TC_PAIR=1 (forced for this small job)
+    and AEC_TC_PAIR=0 must give bit-identical heads, maps, pool state and frontiers.  conv3 (two tiles, pool in its
+    epilogue) and conv4 (four tiles, plain epilogue) take both variants of the pair kernel."""
+    S, steps, h, w = 6, 40, 32, 48
+    wts = P.xavier_weights(PAIR_NET, seed=16)
+    evs = P.synthetic_events("uniform", S, steps, 30, h, w, seed=12)
+    nets = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AEC_TC_PAIR", flag)
+        nets.append(EventNetCuda(h, w, PAIR_NET, wts, 5e-5, 0.1, "SAME", n_streams=S))
+    for t in range(steps):
+        per = [evs[s, t] for s in range(S)]
+        ha, hb = nets[0].step(per), nets[1].step(per)
+        assert np.array_equal(ha, hb), "step %d head" % t
+        if t % 8 == 7 or t == steps - 1:
+            for s in range(S):
+                for i in range(len(nets[0].names)):
+                    sa, sb = nets[0].state(i, s), nets[1].state(i, s)
+                    for key in sa:
+                        assert np.array_equal(sa[key], sb[key]), "step %d stream %d layer %s %s" % (t, s, nets[0].names[i], key)
+                    assert np.array_equal(nets[0].frontier(i, s), nets[1].frontier(i, s))
+    for n in nets:
+        n.close()
+
+
+def test_pair_units_exact_against_oracle(monkeypatch):
+    """The CTA-pair kernel against the oracle on exactly representable arithmetic (bit-equal maps, argmax rows, flags and
+    frontiers; conv3 of the net has two weight tiles and the pool in its epilogue): conv2d.py:118-123,144-181, maxpool.py:118-151."""
+    monkeypatch.setenv("AEC_TC_PAIR", "1")
+    S, steps, h, w = 3, 30, 32, 48
+    wts = P.xavier_weights(POOL_IN_CONV, seed=31, exact=True)
+    evs = P.synthetic_events("edge", S, steps, 24, h, w, seed=33, dt_int=(1, 5))
+    net = EventNetCuda(h, w, POOL_IN_CONV, wts, 1.0 / 64, 0.5, "SAME", n_streams=S)
+    oracles = [OracleEventNet(h, w, POOL_IN_CONV, wts, 1.0 / 64, 0.5, "SAME") for _ in range(S)]
+    for t in range(steps):
+        per = [evs[s, t] if (s + 2 * t) % 7 else None for s in range(S)]
+        heads = net.step(per)
+        for s in range(S):
+            if per[s] is None:
+                continue
+            assert np.array_equal(heads[s], oracles[s].step(per[s])), "step %d stream %d head" % (t, s)
+        if t % 5 == 4:
+            for s in range(S):
+                oa = OracleAdapter(oracles[s])
+                for i in range(len(net.names)):
+                    so, sc = oa.state(i), net.state(i, s)
+                    for key in so:
+                        assert np.array_equal(sc[key], so[key]), "step %d stream %d layer %s %s" % (t, s, net.names[i], key)
+                    if per[s] is not None:
+                        assert np.array_equal(net.frontier(i, s), oa.frontier(i))
+    net.close()
+
+
 def test_half_units_change_no_bit(monkeypatch):
     """With few sites on a layer's work list the gathered kernel cuts units of 64 sites (one MMA of N = 128 per product)
     instead of 128, so that more CTAs work on a small job.  Same accumulation order per site: AEC_TC_HALF=0 (always 128-site
