@@ -99,6 +99,7 @@ struct aec_net {
     bool sweep_skip = true;              // the leak sweep leaves the sites alone that the step re-evaluates (AEC_SWEEP_SKIP=0: leak every live site)
     bool tc_half = true, rt_store32 = true;   // developer switches read at finalize (AEC_TC_HALF, AEC_RT_STORE32)
     int tc_pair_mode = -1;                    // AEC_TC_PAIR: 0 never, 1 wherever the layer allows it, unset (-1): from 32 streams on
+    bool pdl = false;                         // AEC_PDL=1: programmatic dependent launch for the kernels of the step (measured slower: 3.73 vs 3.66 ms)
     FrontLayer *front_table = nullptr;   // device copy of the per-layer frontier descriptors (k_frontier_all)
     int front_max_words = 0;
     int *counts = nullptr, *err_flag = nullptr;
@@ -480,6 +481,31 @@ static Src make_src(const aec_net *n, int li)
     return q;
 }
 
+// Every kernel of the step goes through here: with n->pdl the launch carries the programmatic-serialization attribute
+// (the kernels start with pdl_enter(), aec_kernels.cuh), `cluster` > 1 launches thread-block clusters.  Errors are picked
+// up by launch_check (cudaGetLastError).
+template <typename P>
+static void launch_k(const aec_net *n, void (*fn)(P), dim3 grid, unsigned block, size_t smem, cudaStream_t st, const P &p, int cluster = 1)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    unsigned na = 0;
+    if (n->pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    (void)cudaLaunchKernelEx(&cfg, fn, p);
+}
+
 static int launch_check(aec_net *n, const char *what)
 {
     cudaError_t e = cudaGetLastError();
@@ -542,7 +568,7 @@ static int run_integrate(aec_net *n, const int32_t *ev, const int32_t *off, cuda
     const size_t smem = (size_t)n->hash_slots * 8 + (size_t)l.H * l.Ww * 8;
     int rc;
     if ((rc = prof_mark(n, st))) return rc;
-    k_integrate<<<n->S, kThreads, smem, st>>>(p);
+    launch_k(n, k_integrate, n->S, kThreads, smem, st, p);
     if ((rc = launch_check(n, "k_integrate"))) return rc;
     return prof_mark(n, st, "surface");
 }
@@ -573,13 +599,13 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
         int rc = AEC_OK;
         if (n->sweep_win_chunks > 0) {
             dim3 gridw(n->sweep_win_chunks, n->S);
-            k_sweep_windows<<<gridw, kThreads, 0, st>>>(n->sweep_win);
+            launch_k(n, k_sweep_windows, gridw, kThreads, 0, st, n->sweep_win);
             if ((rc = launch_check(n, "k_sweep_windows"))) return rc;
             if ((rc = prof_mark(n, st, "window_sweep"))) return rc;
         }
         if (n->sweep_all.n_layers == 0) return AEC_OK;
         dim3 grid(n->sweep_chunks, n->S);
-        k_leak_sweep<<<grid, kThreads, 0, st>>>(n->sweep_all);
+        launch_k(n, k_leak_sweep, grid, kThreads, 0, st, n->sweep_all);
         rc = launch_check(n, "k_leak_sweep");
         return rc ? rc : prof_mark(n, st, "leak_sweep");
     }
@@ -588,22 +614,8 @@ static int run_sweep(aec_net *n, int only_layer, cudaStream_t st)
     const int chunks = fill_sweep_layer(n->L[only_layer], p.L[0], 0);
     p.n_layers = 1; p.delta = n->delta; p.active = n->active;
     dim3 grid(chunks, n->S);
-    k_leak_sweep<<<grid, kThreads, 0, st>>>(p);
+    launch_k(n, k_leak_sweep, grid, kThreads, 0, st, p);
     return launch_check(n, "k_leak_sweep");
-}
-
-// CTA-pair form: clusters of two CTAs (one TPC), launched through the extensible API (captured into the step graph like any launch)
-static int launch_tc_pair(void (*fn)(const tc::TcParams), const HostLayer &l, cudaStream_t st, const tc::TcParams &p)
-{
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)l.tc_blocks); cfg.blockDim = dim3(tc::kTcThreads); cfg.dynamicSmemBytes = l.tc_smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, fn, p));
-    return AEC_OK;
 }
 
 static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step)
@@ -633,13 +645,13 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step
         p.quad_bit = 0x80000000u; p.site_counter = n->counts + 32 + li;
         p.pool_idx = pl.idx; p.pool_Fp = pl.Fp; p.pool_Ap = pl.Ap; p.pool_stride = pl.fstride; p.pool_flags = pl.flags;
         p.pool_accum = n->accum + (li + 1); p.pW = pl.W; p.pWw = pl.Ww; p.pHWw = pl.H * pl.Ww; p.pool_alpha = l.alpha;
-        if (l.tc_pair) { if (int rc = launch_tc_pair(tc::k_conv_eval_tc<true, false, true, true>, l, st, p)) return rc; }
-        else tc::k_conv_eval_tc<true, false, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+        if (l.tc_pair) launch_k(n, tc::k_conv_eval_tc<true, false, true, true>, l.tc_blocks, tc::kTcThreads, l.tc_smem, st, p, 2);
+        else launch_k(n, tc::k_conv_eval_tc<true, false, true>, l.tc_blocks, tc::kTcThreads, l.tc_smem, st, p);
     } else
-    if (l.tc_pair) { if (int rc = launch_tc_pair(tc::k_conv_eval_tc<true, false, false, true>, l, st, p)) return rc; }
-    else if (l.tc_sm) tc::k_conv_eval_tc<true, true><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
-    else if (l.tc_fast_decode) tc::k_conv_eval_tc<true, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
-    else tc::k_conv_eval_tc<false, false><<<l.tc_blocks, tc::kTcThreads, l.tc_smem, st>>>(p);
+    if (l.tc_pair) launch_k(n, tc::k_conv_eval_tc<true, false, false, true>, l.tc_blocks, tc::kTcThreads, l.tc_smem, st, p, 2);
+    else if (l.tc_sm) launch_k(n, tc::k_conv_eval_tc<true, true>, l.tc_blocks, tc::kTcThreads, l.tc_smem, st, p);
+    else if (l.tc_fast_decode) launch_k(n, tc::k_conv_eval_tc<true, false>, l.tc_blocks, tc::kTcThreads, l.tc_smem, st, p);
+    else launch_k(n, tc::k_conv_eval_tc<false, false>, l.tc_blocks, tc::kTcThreads, l.tc_smem, st, p);
     int rc = launch_check(n, "k_conv_eval_tc");
     return rc ? rc : prof_mark(n, st, "eval", li);
 }
@@ -670,10 +682,10 @@ static int run_conv_rows(aec_net *n, int li, cudaStream_t st)
     p.timing = n->tc_timing_on ? l.tc_timing : nullptr;
     static const int staged_min = getenv("AEC_RT_STAGED_MIN_C") ? atoi(getenv("AEC_RT_STAGED_MIN_C")) : 33;
     const bool staged = l.C >= staged_min;   // epilogue stores through the per-warp transpose buffer (aec_rt.cuh)
-    if (l.rt_CB == 32 && staged) rt::k_conv_rows<32, true><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
-    else if (l.rt_CB == 32) rt::k_conv_rows<32, false><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
-    else if (staged) rt::k_conv_rows<16, true><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
-    else rt::k_conv_rows<16, false><<<n->num_sms, rt::kRtThreads, l.rt_smem, st>>>(p);
+    if (l.rt_CB == 32 && staged) launch_k(n, rt::k_conv_rows<32, true>, n->num_sms, rt::kRtThreads, l.rt_smem, st, p);
+    else if (l.rt_CB == 32) launch_k(n, rt::k_conv_rows<32, false>, n->num_sms, rt::kRtThreads, l.rt_smem, st, p);
+    else if (staged) launch_k(n, rt::k_conv_rows<16, true>, n->num_sms, rt::kRtThreads, l.rt_smem, st, p);
+    else launch_k(n, rt::k_conv_rows<16, false>, n->num_sms, rt::kRtThreads, l.rt_smem, st, p);
     int rc = launch_check(n, "k_conv_rows");
     return rc ? rc : prof_mark(n, st, "eval", li);
 }
@@ -690,8 +702,8 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = 
         p.S = n->surface; p.sstride = (long long)n->L[0].H * n->L[0].W; p.Hin = n->L[0].H; p.Win = n->L[0].W;
         p.wgt = l.wgt; p.bias = l.bias; p.Npad = l.Npad; p.F = l.F; p.A = l.A; p.fstride = l.fstride;
         p.C = l.C; p.H = l.H; p.W = l.W; p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
-        if (l.kh == 3 && l.kw == 3) k_conv_stencil<3, 3><<<n->num_sms * 8, kThreads, 0, st>>>(p);
-        else k_conv_stencil<0, 0><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+        if (l.kh == 3 && l.kw == 3) launch_k(n, k_conv_stencil<3, 3>, n->num_sms * 8, kThreads, 0, st, p);
+        else launch_k(n, k_conv_stencil<0, 0>, n->num_sms * 8, kThreads, 0, st, p);
         int rc = launch_check(n, "k_conv_stencil");
         return rc ? rc : prof_mark(n, st, "eval", li);
     }
@@ -702,10 +714,10 @@ static int run_conv_eval(aec_net *n, int li, cudaStream_t st, bool fused_step = 
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.Kpad = l.Kpad; p.Npad = l.Npad;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
     switch (l.BN) {
-    case 16: k_conv_eval<16, 2, 4, 16><<<n->conv_eval_blocks[0], kThreads, 0, st>>>(p); break;
-    case 32: k_conv_eval<32, 4, 4, 16><<<n->conv_eval_blocks[1], kThreads, 0, st>>>(p); break;
-    case 64: k_conv_eval<64, 4, 8, 16><<<n->conv_eval_blocks[2], kThreads, 0, st>>>(p); break;
-    default: k_conv_eval<128, 8, 8, 16><<<n->conv_eval_blocks[3], kThreads, 0, st>>>(p); break;
+    case 16: launch_k(n, k_conv_eval<16, 2, 4, 16>, n->conv_eval_blocks[0], kThreads, 0, st, p); break;
+    case 32: launch_k(n, k_conv_eval<32, 4, 4, 16>, n->conv_eval_blocks[1], kThreads, 0, st, p); break;
+    case 64: launch_k(n, k_conv_eval<64, 4, 8, 16>, n->conv_eval_blocks[2], kThreads, 0, st, p); break;
+    default: launch_k(n, k_conv_eval<128, 8, 8, 16>, n->conv_eval_blocks[3], kThreads, 0, st, p); break;
     }
     int rc = launch_check(n, "k_conv_eval");
     return rc ? rc : prof_mark(n, st, "eval", li);
@@ -720,9 +732,9 @@ static int run_pool_eval(aec_net *n, int li, cudaStream_t st)
     p.F = c.F; p.A = c.A; p.fstride = c.fstride; p.alpha = c.alpha; p.cW = c.W;
     p.idx = l.idx; p.Fp = l.Fp; p.Ap = l.Ap; p.pstride = l.fstride; p.flags = l.flags;
     p.C = l.C; p.H = l.H; p.W = l.W; p.Ww = l.Ww; p.kh = l.kh; p.kw = l.kw; p.stride = l.stride; p.code = l.code;
-    if (l.C % 4 == 0 && l.kh == 2 && l.kw == 2 && l.stride == 2) k_pool_eval<4, true><<<n->num_sms * 8, kThreads, 0, st>>>(p);
-    else if (l.C % 4 == 0) k_pool_eval<4, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
-    else k_pool_eval<1, false><<<n->num_sms * 8, kThreads, 0, st>>>(p);
+    if (l.C % 4 == 0 && l.kh == 2 && l.kw == 2 && l.stride == 2) launch_k(n, k_pool_eval<4, true>, n->num_sms * 8, kThreads, 0, st, p);
+    else if (l.C % 4 == 0) launch_k(n, k_pool_eval<4, false>, n->num_sms * 8, kThreads, 0, st, p);
+    else launch_k(n, k_pool_eval<1, false>, n->num_sms * 8, kThreads, 0, st, p);
     int rc = launch_check(n, "k_pool_eval");
     return rc ? rc : prof_mark(n, st, "eval", li);
 }
@@ -741,7 +753,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
         p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
         p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
         const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)pv.H * l.Ww + (size_t)l.H * l.Ww) * 4;
-        k_conv_frontier<<<n->S, kThreads, smem, st>>>(p);
+        launch_k(n, k_conv_frontier, n->S, kThreads, smem, st, p);
         if ((rc = launch_check(n, "k_conv_frontier"))) return rc;
         if ((rc = prof_mark(n, st, "frontier", li))) return rc;
         return run_conv_eval(n, li, st);
@@ -753,7 +765,7 @@ static int run_layer(aec_net *n, int li, bool with_sweep, cudaStream_t st)
     p.Hin = pv.H; p.Win = pv.W; p.WwIn = pv.Ww; p.H = l.H; p.W = l.W; p.Ww = l.Ww;
     p.kh = l.kh; p.kw = l.kw; p.stride = l.stride; p.code = l.code;
     const size_t smem = ((size_t)pv.H * pv.Ww + (size_t)l.H * l.Ww) * 4;
-    k_pool_frontier<<<n->S, kThreads, smem, st>>>(p);
+    launch_k(n, k_pool_frontier, n->S, kThreads, smem, st, p);
     if ((rc = launch_check(n, "k_pool_frontier"))) return rc;
     if ((rc = prof_mark(n, st, "frontier", li))) return rc;
     return run_pool_eval(n, li, st);
@@ -771,7 +783,7 @@ static int run_frontier_skip(aec_net *n, cudaStream_t st)
     p.layers = n->front_table; p.n_layers = (int)n->L.size();
     p.front0 = n->L[0].front; p.nzr0 = n->L[0].nzr; p.words0 = n->L[0].H * n->L[0].Ww;
     p.max_words = n->front_max_words; p.active = n->active;
-    k_frontier_skip<<<n->S, kThreads, (size_t)3 * n->front_max_words * 4, st>>>(p);
+    launch_k(n, k_frontier_skip, n->S, kThreads, (size_t)3 * n->front_max_words * 4, st, p);
     int rc = launch_check(n, "k_frontier_skip");
     return rc ? rc : prof_mark(n, st, "skip.frontier");
 }
@@ -782,7 +794,7 @@ static int run_frontier_all(aec_net *n, cudaStream_t st)
     p.layers = n->front_table; p.n_layers = (int)n->L.size();
     p.front0 = n->L[0].front; p.nzr0 = n->L[0].nzr; p.words0 = n->L[0].H * n->L[0].Ww;
     p.max_words = n->front_max_words; p.active = n->active;
-    k_frontier_all<<<n->S, kThreads, (size_t)5 * n->front_max_words * 4, st>>>(p);
+    launch_k(n, k_frontier_all, n->S, kThreads, (size_t)5 * n->front_max_words * 4, st, p);
     int rc = launch_check(n, "k_frontier_all");
     return rc ? rc : prof_mark(n, st, "all.frontier");
 }
@@ -802,7 +814,7 @@ static int run_head(aec_net *n, cudaStream_t st)
     n->head_last = p.out;
     long long total = (long long)n->head_per_stream * n->S;
     int blocks = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)n->num_sms * 8);
-    k_head<<<blocks, kThreads, 0, st>>>(p);
+    launch_k(n, k_head, blocks, kThreads, 0, st, p);
     int rc = launch_check(n, "k_head");
     return rc ? rc : prof_mark(n, st, "head");
 }
@@ -967,6 +979,7 @@ extern "C" int aec_net_finalize(aec_net *n)
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy
     { const char *e = getenv("AEC_TC_DEBUG"); n->tc_debug = e ? atoi(e) : 0; }
     { const char *e = getenv("AEC_TC_HALF"); n->tc_half = !(e && atoi(e) == 0); }            // 64-site units for small work lists (aec_tc.cuh)
+    { const char *e = getenv("AEC_PDL"); n->pdl = e && atoi(e) != 0; }
     { const char *e = getenv("AEC_TC_PAIR"); n->tc_pair_mode = e ? (atoi(e) != 0) : -1; }      // CTA pairs for layers with 2, 4, ... weight tiles
     { const char *e = getenv("AEC_RT_STORE32"); n->rt_store32 = !(e && atoi(e) == 0); }      // 32-byte epilogue stores (aec_rt.cuh)
     memset(&n->sweep_all, 0, sizeof n->sweep_all);

@@ -34,6 +34,17 @@
 
 namespace aec {
 
+// Programmatic dependent launch: every kernel of the step starts with this.  Launched with the programmatic-serialization
+// attribute (aec.cu: launch_k) a kernel may be scheduled while its predecessor in the stream is still draining - its CTAs take
+// the SMs as they become free and wait here until the predecessor grid has completed and its writes are visible; then they
+// allow the next kernel of the chain to be scheduled the same way.  Without the attribute both instructions do nothing.
+// Measured (profiles/r2_summary.md, finding 14): no gain for one stream (0.233 vs 0.236 ms) and a loss for many (1024 streams:
+// 3.73 vs 3.66 ms per step) - the step is not bound by launch gaps - so the attribute is off unless AEC_PDL=1.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory");
+}
+
 constexpr int kThreads = 256;
 constexpr int kMaxConv = 24;           // conv layers per network
 constexpr int kMaxSweep = 2 * kMaxConv;  // leak-sweep table: conv maps + pooled copies
@@ -332,6 +343,7 @@ struct IntegrateParams {
 
 __global__ void __launch_bounds__(kThreads) k_integrate(IntegrateParams p)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *hkey = reinterpret_cast<int *>(smem_raw);
     int *hval = hkey + p.hash_slots;
@@ -569,6 +581,7 @@ __device__ __forceinline__ void pool_next(PoolBest &b, int row, float f, float a
 // Its own kernel (grid: chunks x S) so that the plain sweep keeps its 48 registers per thread.
 __global__ void __launch_bounds__(kThreads, 4) k_sweep_windows(const __grid_constant__ SweepWindowsParams p)
 {
+    pdl_enter();
     __shared__ int s_win[kSweepMaxWords * 32];
     __shared__ int s_scan[9];
     const int s = blockIdx.y;
@@ -704,6 +717,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_windows(const __grid_cons
 
 __global__ void __launch_bounds__(kThreads) k_leak_sweep(const __grid_constant__ SweepParams p)
 {
+    pdl_enter();
     __shared__ int s_live[kSweepMaxWords * 32];
     __shared__ int s_scan[9];
     const int s = blockIdx.y;
@@ -830,6 +844,7 @@ struct ConvFrontParams {
 
 __global__ void __launch_bounds__(kThreads) k_conv_frontier(ConvFrontParams p)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *P = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *Hd = P + p.Hin * p.WwIn;
@@ -914,6 +929,7 @@ struct PoolFrontParams {
 
 __global__ void __launch_bounds__(kThreads) k_pool_frontier(PoolFrontParams p)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *P = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *Wb = P + p.Hin * p.WwIn;
@@ -1025,6 +1041,7 @@ __device__ __forceinline__ void stage_front_table(FrontLayer *dst, const FrontLa
 
 __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
 {
+    pdl_enter();
     __shared__ __align__(16) FrontLayer s_layers[kMaxFrontLayers];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);        // previous layer's frontier
@@ -1198,6 +1215,7 @@ __global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_frontier_skip(FrontAllParams p)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);        // previous layer's (flip-free) frontier
     uint32_t *Hd = bufA + p.max_words;                              // scratch (horizontal dilation)
@@ -1298,6 +1316,7 @@ struct PoolEvalParams {
 template <int VEC, bool WIN2>
 __global__ void __launch_bounds__(kThreads) k_pool_eval(PoolEvalParams p)
 {
+    pdl_enter();
     const int n = *p.counter;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.accum, (unsigned long long)n);
     const int CG = p.C / VEC;
@@ -1400,6 +1419,7 @@ struct ConvEvalParams {
 template <int BN, int TN, int TM, int BK>
 __global__ void __launch_bounds__(kThreads) k_conv_eval(ConvEvalParams p)
 {
+    pdl_enter();
     constexpr int TX = BN / TN;            // threads along n
     constexpr int TY = kThreads / TX;      // threads along rows
     constexpr int ROWS = TY * TM;
@@ -1572,6 +1592,7 @@ constexpr int kStencilMaxK = 64, kStencilMaxC = 64;
 template <int KH, int KW>
 __global__ void __launch_bounds__(kThreads) k_conv_stencil(StencilParams p)
 {
+    pdl_enter();
     const int kh = KH > 0 ? KH : p.kh, kw = KW > 0 ? KW : p.kw;
     __shared__ __align__(16) float w_s[kStencilMaxK * kStencilMaxC];
     __shared__ __align__(16) float b_s[kStencilMaxC];
@@ -1631,6 +1652,7 @@ struct HeadParams {
 
 __global__ void __launch_bounds__(kThreads) k_head(HeadParams p)
 {
+    pdl_enter();
     const long long per = (long long)p.src.H * p.src.W * p.src.C;
     const long long total = per * p.S;
     if (p.src.kind == 1 && (per & 1) == 0) {

@@ -102,6 +102,7 @@ __device__ __forceinline__ uint32_t rt_off(int t, int c, int row_bytes)
 template <int kCB, bool kStaged>
 __global__ void __launch_bounds__(kRtThreads, 1) k_conv_rows(const __grid_constant__ RtParams p)
 {
+    pdl_enter();
     extern __shared__ unsigned char rt_smem_raw[];
     // Weights: a layer whose kh*kw*ncb tiles fit (conv2: 36 KB) keeps them RESIDENT - loaded once per CTA, bar_w_full[0] - because a
     // streamed tile travels commit -> loader -> L2 -> shared memory -> gatekeeper in ~4 k cycles (measured, profiles/r2_summary.md)

@@ -413,6 +413,7 @@ __device__ __forceinline__ void item_store(const TcParams &p, uint32_t x_hi, uin
 template <bool kFastDecode, bool kSM, bool kPool = false, bool kPair = false>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_constant__ TcParams p)
 {
+    pdl_enter();
     static_assert(!kPool || (kFastDecode && !kSM), "the fused pool lives in the weights-as-M epilogue and the batched decoder");
     static_assert(!kPair || (kFastDecode && !kSM), "CTA pairs: weights-as-M form with the batched decoder");
     extern __shared__ unsigned char tc_smem_raw[];
