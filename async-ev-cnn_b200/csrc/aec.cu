@@ -1639,7 +1639,7 @@ extern "C" int aec_net_tc_geometry(const aec_net *n, int layer, long long *out8)
     } else {
         out8[4] = 3;                                               // W_hi.X_lo + W_lo.X_hi + W_hi.X_hi
         out8[2] = k8 * out8[4] * l.m_tiles * 2LL * 128 * tc::kUnitCols * 8;   // every MMA is M128 x N256 x K8
-        out8[6] = l.tc_fast_decode ? 1 : 0;
+        out8[6] = l.tc_pair ? 4 : l.tc_fast_decode ? 1 : 0;        // pairs: one M = 256 MMA covers two weight tiles - the same FLOPs per unit
     }
     return AEC_OK;
 }

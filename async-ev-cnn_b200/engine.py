@@ -340,7 +340,8 @@ class EventNetCuda:
                 "mma_per_kstep": int(buf[4]), "weight_tiles": int(buf[5]),
                 "units_counted": bool(buf[7]),
                 "kernel": ("k_conv_eval_tc<simple decode, weights-as-M>", "k_conv_eval_tc<batched decode, weights-as-M>",
-                           "k_conv_eval_tc<sites-as-M>", "k_conv_rows (row tiles, sites-as-M)")[int(buf[6])]}
+                           "k_conv_eval_tc<sites-as-M>", "k_conv_rows (row tiles, sites-as-M)",
+                           "k_conv_eval_tc<CTA pairs, cta_group::2 M = 256, weights-as-M>")[int(buf[6])]}
 
     def unit_counters(self):
         """Work units evaluated per layer by the row-tile kernel since the last counters(reset=True)."""

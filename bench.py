@@ -627,13 +627,30 @@ def native_arm(args):
         f["ms"] += row["ms"]
         f["flops"] += layer_flops(net, i, sites_per_step[i])
         f["issued"] += row.get("issued_TFLOPs", 0.0) * row["ms"]
+        f["bytes"] = f.get("bytes", 0.0) + row.get("alg_GB", 0.0) * 1e9
         f["n"] += 1
     dom = max(fam, key=lambda k: fam[k]["ms"]) if fam else "k_conv_eval_tc"
     fd = fam.get(dom, {"ms": 0.0, "flops": 0.0, "issued": 0.0, "n": 1})
     tc_ms = by_kernel.get("conv_eval_tc", 0.0)
     dom_tflops = fd["flops"] / (fd["ms"] * 1e-3) / 1e12 if fd["ms"] > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": dom_tflops, "peak": tf_pk, "unit": "TFLOP/s",
-                "frac": dom_tflops / tf_pk, "traffic": None, "peak_source": tf_src,
+    # Which roof bounds it: arithmetic intensity (useful FLOPs per algorithmic byte) against the ridge of the two measured peaks.
+    # Row tiles (Cout <= 64: 33-72 FLOP/B) sit left of it - the HBM roof is the attainable one - the gathered layers
+    # (Cout >= 128) on it or right of it.  `frac` = attainable time / measured time of the binding roof; both are reported.
+    dom_bytes = fd.get("bytes", 0.0)
+    dom_gbs = dom_bytes / (fd["ms"] * 1e-3) / 1e9 if fd["ms"] > 0 else 0.0
+    intensity = fd["flops"] / dom_bytes if dom_bytes > 0 else float("inf")
+    ridge = tf_pk * 1e12 / (peak * 1e9)
+    hbm_bound = intensity < ridge
+    roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
+                "achieved": dom_gbs if hbm_bound else dom_tflops, "peak": peak if hbm_bound else tf_pk, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                "frac": (dom_gbs / peak) if hbm_bound else (dom_tflops / tf_pk), "traffic": None,
+                "peak_source": (peak_src if hbm_bound else tf_src),
+                "intensity_flop_per_byte": round(intensity, 1), "ridge_flop_per_byte": round(ridge, 1),
+                "bound_rule": "useful FLOPs / algorithmic bytes of the kernel's launches against the ridge tensor peak / HBM peak: left of it the HBM roof "
+                              "is the attainable one, right of it the tensor roof; both fractions follow",
+                "hbm": {"achieved_GBps": round(dom_gbs, 1), "peak_GBps": peak, "frac": round(dom_gbs / peak, 4), "algorithmic_bytes_per_launch": dom_bytes / max(1, fd["n"]),
+                        "peak_source": peak_src},
+                "tensor": {"useful_TFLOPs": round(dom_tflops, 2), "peak_TFLOPs": round(tf_pk, 1), "frac": round(dom_tflops / tf_pk, 4), "peak_source": tf_src},
                 "precision": "3xTF32 (two or three tcgen05.mma.kind::tf32 per product for fp32-grade results): `achieved` counts "
                              "USEFUL FLOPs (2 x sites x {value, rate} x K x Cout); `issued` what the tensor pipe was asked to do, "
                              "padding rows, gap sites of a row tile and split products included",

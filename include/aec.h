@@ -308,7 +308,8 @@ int aec_net_tc_timing(aec_net *net, int enable, int layer, unsigned long long *o
  * roofline table.  out8 = { 1 if the layer runs on the tcgen05 kernel else 0, sites per work unit,
  * tensor FLOPs ISSUED per unit over all weight tiles (every tcgen05.mma counted as 2*M*N*K with its padding rows
  * and all split-precision products), 8-wide K steps, MMAs per K step and weight tile, weight tiles, kernel variant
- * id, 1 if units are counted by aec_net_read_unit_counters (row-tile kernel) }.  Returns 0, or a negative code for a bad layer index.
+ * id (0 / 1 gathered kernel with the simple / batched decoder, 2 its sites-as-M form, 3 row tiles, 4 gathered kernel on
+ * CTA pairs), 1 if units are counted by aec_net_read_unit_counters (row-tile kernel) }.  Returns 0, or a negative code for a bad layer index.
  */
 int aec_net_tc_geometry(const aec_net *net, int layer, long long *out8);
 

@@ -65,14 +65,17 @@ def test_efcn_event_equals_dense_torch_frame_network():
     net.close()
 
 
-@pytest.mark.parametrize("kind", ["edge", "uniform"])
-def test_efcn_benchmark_regime_against_live_oracle(kind):
+@pytest.mark.parametrize("kind,pairs", [("edge", False), ("uniform", False), ("edge", True)])
+def test_efcn_benchmark_regime_against_live_oracle(kind, pairs, monkeypatch):
     """The regime bench.py measures (BASELINE config 2): EFCN 160x224, B = 200, sweep skipping on, compared with the
     live oracle step by step from reset THROUGH the 160-step settling phase and 64 steps of the steady state behind it
     (sticky pool flags saturated, the leak sweep skipping what the step re-evaluates).  Every step: surface and
     surface events exact, the integer decisions bit-exactly the reference's rules on the CUDA path's own maps, float
     maps within 1e-4 of the scale, and any integer difference from the oracle explained by a near tie in the
-    oracle's own values.  The counters of both phases go to the parity log (profiles/parity_r2.json)."""
+    oracle's own values.  The counters of both phases go to the parity log (profiles/parity_r2.json).
+    `pairs`: with 32 streams or more (the benchmark has 1024) conv5 and conv6 run on CTA pairs (tcgen05 cta_group::2: aec_tc.cuh kPair); AEC_TC_PAIR=1 selects those kernels for the two streams of this test."""
+    if pairs:
+        monkeypatch.setenv("AEC_TC_PAIR", "1")
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from parity import OracleAdapter, compare_live, record_parity
@@ -85,9 +88,13 @@ def test_efcn_benchmark_regime_against_live_oracle(kind):
     ora = OracleEventNet(H, W, P.EFCN_LAYERS, wts, 5e-5, 0.1, "SAME")
     ad, oa = CudaAdapter(net, stream=1), OracleAdapter(ora)
     a = compare_live(ad, oa, list(evs[:settle]), exact=False)
-    record_parity("live/efcn160x224_%s_steps0-%d_settling" % (kind, settle - 1), a)
+    tag = kind + ("_cta_pairs" if pairs else "")
+    record_parity("live/efcn160x224_%s_steps0-%d_settling" % (tag, settle - 1), a)
     b = compare_live(ad, oa, list(evs[settle:]), exact=False, carry=a.carry)
-    record_parity("live/efcn160x224_%s_steps%d-%d_steady_state" % (kind, settle, settle + steady - 1), b)
+    record_parity("live/efcn160x224_%s_steps%d-%d_steady_state" % (tag, settle, settle + steady - 1), b)
+    if pairs:
+        kernels = [g["kernel"] for g in (net.tc_geometry(i) for i in range(1, len(net.names))) if g is not None]
+        assert sum("CTA pairs" in k for k in kernels) == 2, kernels
     st = net.sweep_stats()
     assert st["swept_conv_elems"] < st["live_conv_elems"], "the steady state is where the sweep skips work"
     net.close()
