@@ -631,6 +631,11 @@ static int run_conv_eval_tc(aec_net *n, int li, cudaStream_t st, bool fused_step
     p.C = l.C; p.H = l.H; p.W = l.W; p.K = l.K; p.KB = l.KB; p.ks_last = (l.K - tc::kBlockK * (l.KB - 1) + 7) / 8; p.Mrows = l.Mrows; p.Mch = l.Mch; p.rep = l.rep; p.m_tiles = l.m_tiles; p.mtu = l.mtu;
     p.kh = l.kh; p.kw = l.kw; p.pad_t = l.pad_t; p.pad_l = l.pad_l; p.code = l.code;
     p.w_stages = l.w_stages; p.n_acc = l.n_acc;
+    {
+        // half units: 96 KB of site stages; what the launch's shared memory holds beyond them is weight stages
+        const size_t w_stage = 2 * (size_t)l.Mrows * 128, x_half = (size_t)tc::kPairSiteStages * 2 * tc::kItemTileBytes;
+        p.w_stages_half = (int)std::min<size_t>(tc::kMaxWStages, (l.tc_smem - 1024 - x_half) / w_stage);
+    }
     p.half_units = n->tc_half ? 1 : 0;
     p.quad_bit = 0u; p.site_counter = nullptr; p.pool_idx = nullptr; p.pool_Fp = p.pool_Ap = nullptr; p.pool_stride = 0; p.pool_flags = nullptr;
     p.pool_accum = nullptr; p.pW = p.pWw = p.pHWw = 0; p.pool_alpha = 1.f;

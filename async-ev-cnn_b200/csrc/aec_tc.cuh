@@ -76,8 +76,8 @@ constexpr int kItemTileBytes = 128 * 128;      // one item's hi (or lo) rows: 12
 constexpr int kSiteTileBytes = 2 * kItemTileBytes;   // hi (or lo) tile of a site stage: 256 rows
 constexpr int kSiteStageBytes = 2 * kSiteTileBytes;  // hi + lo
 constexpr int kSiteStages = 2;
-constexpr int kMaxSiteStages = 4;              // half-unit mode: every item slot of the two stages is a stage of its own
-constexpr int kPairSiteStages = 3;             // CTA pairs: three one-item stages of 32 KB (hi, lo), the rest of the shared memory holds weight stages
+constexpr int kMaxSiteStages = 4;              // barrier array size
+constexpr int kPairSiteStages = 3;             // one-item stages (half units, CTA pairs): three of 32 KB (hi, lo); the rest of the shared memory holds weight stages
 constexpr int kMaxWStages = 4;
 constexpr int kMaxMtu = 2;                     // weight tiles per unit (2 x 256 accumulator columns)
 constexpr int kSiteRing = 4;                   // site-info buffers: producers may run this many units ahead of the epilogue
@@ -270,6 +270,7 @@ struct TcParams {
     int kh, kw, pad_t, pad_l;
     SiteCode code;              // work-list entry coding of the output layer
     int w_stages;               // weight pipeline depth
+    int w_stages_half;          // ... when the launch runs on half units (three 32 KB site stages instead of 128 KB: more weight stages fit)
     int n_acc;                  // accumulator buffers in TMEM (2 when mtu == 1, else 1)
     // kPool (weights-as-M only): the 2x2 / stride-2 pool behind this layer is evaluated here for the windows that arrive as quads
     // (four consecutive work-list entries, the first flagged with quad_bit: emit_sites_quads) - maxpool.py:130-151, cutils.pyx:161-177
@@ -446,24 +447,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
     // Site stages: two of two items each, or - half units - the same four item slots as four one-item stages.  Three producer
     // groups take the items round-robin, so a group's consecutive items are three apart: with fewer than three stages it
     // could reach a stage TWO uses ahead of its consumer, and a parity wait cannot tell "two phases behind" from "done".
-    const uint32_t n_xst = kPair ? (uint32_t)kPairSiteStages : one_item ? (uint32_t)kMaxSiteStages : (uint32_t)kSiteStages;
+    // One-item stages (half units, pairs) use the compact layout: three stages of 32 KB (hi tile, lo tile behind it), and the 32 KB
+    // that frees go to the weight ring.  For pairs the third weight stage is what made them pay (conv5 0.60 -> 0.50 ms); for half
+    // units (one stream) it is neutral: a lone SM streams its weight image at ~23 bytes per cycle however many bulk copies it
+    // has in flight (conv5: 1.18 MB per CTA = the 52 k cycles the launch takes, profiles/r2_summary.md finding 15).
+    const uint32_t n_xst = one_item ? (uint32_t)kPairSiteStages : (uint32_t)kSiteStages;
+    const int w_stages = (half && !kPair) ? p.w_stages_half : p.w_stages;
     // first byte of site stage sx (its hi tile; the lo tile is kSiteTileBytes behind): item slot (sx >> 1, sx & 1) when a stage is one item
-    constexpr uint32_t kLoOff = kPair ? (uint32_t)kItemTileBytes : (uint32_t)kSiteTileBytes;      // from a stage's hi tile to its lo tile
-    auto stage_off = [&](uint32_t sx) { return kPair ? sx * 2u * (uint32_t)kItemTileBytes : one_item ? (sx >> 1) * (uint32_t)kSiteStageBytes + (sx & 1u) * (uint32_t)kItemTileBytes : sx * (uint32_t)kSiteStageBytes; };
+    const uint32_t kLoOff = one_item ? (uint32_t)kItemTileBytes : (uint32_t)kSiteTileBytes;      // from a stage's hi tile to its lo tile
+    auto stage_off = [&](uint32_t sx) { return one_item ? sx * 2u * (uint32_t)kItemTileBytes : sx * (uint32_t)kSiteStageBytes; };
     const int n_blocks = (n_sites + usites - 1) / usites;
     const int total_units = n_blocks * n_mgroups;
     if (worker >= total_units) return;                // uniform per CTA (and per pair): nothing allocated yet
 
     unsigned char *smem_w = reinterpret_cast<unsigned char *>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t w_tile = (uint32_t)p.Mrows * 128u;             // one weight tile (hi or lo)
-    unsigned char *smem_x = smem_w + (size_t)p.w_stages * 2 * w_tile;
+    unsigned char *smem_x = smem_w + (size_t)w_stages * 2 * w_tile;
 
     if (tid == 0) {
         for (int i = 0; i < (int)n_xst; ++i) {
             mbar_init(smem_u32(&bar_x_full[i]), (uint32_t)(ipk * kGroupThreads));   // every item of the stage (one producer group each)
             mbar_init(smem_u32(&bar_x_empty[i]), 1);
         }
-        for (int i = 0; i < p.w_stages; ++i) {
+        for (int i = 0; i < w_stages; ++i) {
             mbar_init(smem_u32(&bar_w_full[i]), 1);
             mbar_init(smem_u32(&bar_w_empty[i]), 1);
         }
@@ -731,7 +737,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 const uint32_t sx = qx % n_xst;
                 const uint32_t x_hi = x_base + stage_off(sx), x_lo = x_hi + kLoOff;
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
-                    const uint32_t sw = qw % (uint32_t)p.w_stages;
+                    const uint32_t sw = qw % (uint32_t)w_stages;
                     const uint32_t w_hi = w_base + sw * 2u * w_tile, w_lo = w_hi + w_tile;
                     const uint32_t d = tmem_base + (uint32_t)((ab * p.mtu + mt) * kUnitCols);
                     const int ks_n = kb == p.KB - 1 ? p.ks_last : kBlockK / 8;
@@ -815,10 +821,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 const uint32_t sx = qx % n_xst;
                 const uint32_t px = (qx / n_xst) & 1u;
                 for (int mt = 0; mt < mt_count; ++mt, ++qw) {
-                    const uint32_t sw = qw % (uint32_t)p.w_stages;
+                    const uint32_t sw = qw % (uint32_t)w_stages;
                     // every wait costs ~170 cycles even when the barrier is already complete: the weights (normally early)
                     // first, the site stage (normally the last thing to arrive) last, one barrier for both of its halves
-                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)p.w_stages) & 1u, timing, tw_w);
+                    timed_wait(smem_u32(&bar_w_full[sw]), (qw / (uint32_t)w_stages) & 1u, timing, tw_w);
                     if (mt == 0) timed_wait(smem_u32(&bar_x_full[sx]), px, timing, tw_x);
                     if constexpr (kPair) {
                         // The peer relays: everything of pass qw on its side is ready -> bar_peer[qw & 3] of the leader.  It can be
@@ -853,8 +859,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_eval_tc(const __grid_con
                 const int mt_count = tiles_of(mg);
                 for (int kb = 0; kb < p.KB; ++kb) {
                     for (int mt = 0; mt < mt_count; ++mt, ++qw) {
-                        const int sw = (int)(qw % (uint32_t)p.w_stages);
-                        const uint32_t use = qw / (uint32_t)p.w_stages;
+                        const int sw = (int)(qw % (uint32_t)w_stages);
+                        const uint32_t use = qw / (uint32_t)w_stages;
                         if (use > 0) timed_wait(smem_u32(&bar_w_empty[sw]), (use - 1) & 1u, timing, tw_w);
                         const float *src = p.wimg + ((size_t)(tile0_of(mg) + mt) * p.KB + kb) * tile_floats;
                         if (p.debug & 16) { mbar_arrive(smem_u32(&bar_w_full[sw])); continue; }
