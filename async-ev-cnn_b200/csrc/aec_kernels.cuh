@@ -1039,7 +1039,10 @@ __device__ __forceinline__ void stage_front_table(FrontLayer *dst, const FrontLa
     for (int i = threadIdx.x; i < words; i += kThreads) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
 }
 
-__global__ void __launch_bounds__(kThreads) k_frontier_all(FrontAllParams p)
+// kMinBlocks = 8 caps the kernel at 32 registers (a few spills): eight CTAs per SM instead of six, i.e. ONE wave for the 1024 streams of the
+// benchmark instead of 888 + 136 (0.133 -> 0.096 ms); with few streams the spills only cost (one stream 56 -> 60 us): the host picks.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllParams p)
 {
     pdl_enter();
     __shared__ __align__(16) FrontLayer s_layers[kMaxFrontLayers];
