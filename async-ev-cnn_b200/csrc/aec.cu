@@ -801,7 +801,8 @@ static int run_frontier_all(aec_net *n, cudaStream_t st)
     p.max_words = n->front_max_words; p.active = n->active;
     // more streams than fit one wave at the kernel's natural register count (6 CTAs per SM): the 32-register build (8 per SM)
     if (n->S > 6 * n->num_sms) launch_k(n, k_frontier_all<8>, n->S, kThreads, (size_t)5 * n->front_max_words * 4, st, p);
-    else launch_k(n, k_frontier_all<6>, n->S, kThreads, (size_t)5 * n->front_max_words * 4, st, p);
+    else if (n->S > 4 * n->num_sms) launch_k(n, k_frontier_all<6>, n->S, kThreads, (size_t)5 * n->front_max_words * 4, st, p);
+    else launch_k(n, k_frontier_all<4, true>, n->S, kThreads, (size_t)5 * n->front_max_words * 4, st, p);      // few streams: bitmaps prefetched a layer ahead
     int rc = launch_check(n, "k_frontier_all");
     return rc ? rc : prof_mark(n, st, "all.frontier");
 }
@@ -985,6 +986,7 @@ extern "C" int aec_net_finalize(aec_net *n)
         CU(cudaFuncSetAttribute(k_frontier_skip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)3 * mw * 4, 48 * 1024)));
         CU(cudaFuncSetAttribute(k_frontier_all<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)5 * mw * 4, 48 * 1024)));
         CU(cudaFuncSetAttribute(k_frontier_all<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)5 * mw * 4, 48 * 1024)));
+        CU(cudaFuncSetAttribute(k_frontier_all<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>((size_t)5 * mw * 4, 48 * 1024)));
     }
 
     // leak-sweep table: every conv layer's (F, A), then every pool layer's (Fp, Ap) copy

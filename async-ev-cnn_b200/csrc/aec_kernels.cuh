@@ -1041,7 +1041,12 @@ __device__ __forceinline__ void stage_front_table(FrontLayer *dst, const FrontLa
 
 // kMinBlocks = 8 caps the kernel at 32 registers (a few spills): eight CTAs per SM instead of six, i.e. ONE wave for the 1024 streams of the
 // benchmark instead of 888 + 136 (0.133 -> 0.096 ms); with few streams the spills only cost (one stream 56 -> 60 us): the host picks.
-template <int kMinBlocks>
+// kPrefetch (few streams: the chain's LATENCY is the cost, one CTA per stream and SMs to spare): every layer reads two bitmaps
+// from global memory that earlier KERNELS wrote (conv: the sweep's sign flips and the rate bits; pool: the sticky flags and the rate
+// bits) - a dependent round trip of ~1.3 k cycles per layer, and one per loop iteration where stores separate the loads.  They
+// are fetched one layer AHEAD into registers (kFrontPf words of each per thread; longer bitmaps fall back to direct loads).
+constexpr int kFrontPf = 5;
+template <int kMinBlocks, bool kPrefetch = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllParams p)
 {
     pdl_enter();
@@ -1064,6 +1069,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllP
         }
         return;
     }
+    // next layer's {sign flips | sticky flags} and rate bits of this thread's words i = tid + k * kThreads
+    uint32_t pf_a[kPrefetch ? kFrontPf : 1], pf_b[kPrefetch ? kFrontPf : 1];
+    auto prefetch = [&](int lj) {
+        if constexpr (kPrefetch) {
+            if (lj >= p.n_layers) return;
+            const FrontLayer &Ln = s_layers[lj];
+            const int n = Ln.H * Ln.Ww;
+            const uint32_t *ga = (Ln.type == 1 ? Ln.signchg : Ln.flags) + (long long)s * n;
+            const uint32_t *gb = Ln.nzr + (long long)s * n;
+#pragma unroll
+            for (int k = 0; k < kFrontPf; ++k) {
+                const int i = tid + k * kThreads;
+                pf_a[k] = i < n ? ga[i] : 0u;
+                pf_b[k] = i < n ? gb[i] : 0u;
+            }
+        }
+    };
+    prefetch(1);
     for (int i = tid; i < p.words0; i += kThreads) {
         bufA[i] = p.front0[(long long)s * p.words0 + i];
         bufB[i] = p.nzr0[(long long)s * p.words0 + i];
@@ -1072,6 +1095,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllP
     for (int li = 1; li < p.n_layers; ++li) {
         const FrontLayer &L = s_layers[li];
         const int nout = L.H * L.Ww;
+        uint32_t cur_a[kPrefetch ? kFrontPf : 1], cur_b[kPrefetch ? kFrontPf : 1];
+        if constexpr (kPrefetch) {
+#pragma unroll
+            for (int k = 0; k < kFrontPf; ++k) { cur_a[k] = pf_a[k]; cur_b[k] = pf_b[k]; }
+            prefetch(li + 1);
+        }
+        // runs body(i, a, b) for this thread's words: a = the layer's sign-flip / flag word i, b = its rate-bit word i
+        auto for_words = [&](const uint32_t *ga, const uint32_t *gb, auto body) {
+            if constexpr (kPrefetch) {
+#pragma unroll
+                for (int k = 0; k < kFrontPf; ++k) {
+                    const int i = tid + k * kThreads;
+                    if (i < nout) body(i, cur_a[k], cur_b[k]);
+                }
+                for (int i = tid + kFrontPf * kThreads; i < nout; i += kThreads) body(i, ga[i], gb[i]);
+            } else {
+                for (int i = tid; i < nout; i += kThreads) body(i, ga[i], gb[i]);
+            }
+        };
         const uint32_t lastmask = (L.W & 31) ? ((1u << (L.W & 31)) - 1u) : 0xffffffffu;
         uint32_t *front = L.front + (long long)s * nout;
         uint32_t *nz = L.nzr + (long long)s * nout;
@@ -1101,17 +1143,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllP
             __syncthreads();
             hdilate(bufB);
             __syncthreads();
-            for (int i = tid; i < nout; i += kThreads) {
+            for_words(sc, nz, [&](int i, uint32_t flips, uint32_t z) {
                 const uint32_t n = N[i];
-                const uint32_t flips = sc[i];
                 if (flips) sc[i] = 0u;
                 const uint32_t f = n | flips;
                 front[i] = f;
-                uint32_t z = nz[i];
                 if (n) { z = (z & ~n) | (n & vdilate(i)); nz[i] = z; }
                 Z[i] = z;
                 bufA[i] = f;          // safe: bufA was last read by the first hdilate, two barriers ago
-            }
+            });
             __syncthreads();
         } else {
             uint32_t *fl = L.flags + (long long)s * nout;
@@ -1143,9 +1183,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllP
             };
             const uint32_t *pskip = L.swp_uns ? L.swp_skip + (long long)s * L.Hin * L.WwIn : nullptr;
             uint32_t *uns = L.swp_uns ? L.swp_uns + (long long)s * nout : nullptr;
-            for (int i = tid; i < nout; i += kThreads) {
+            for_words(fl, nz, [&](int i, uint32_t before, uint32_t z) {
                 const uint32_t hit = window_or(bufA, i);
-                const uint32_t before = fl[i];
                 uint32_t f = before & ~hit;           // maxpool.py:118-120
                 const uint32_t wset = hit | f;        // maxpool.py:123-126
                 uint32_t todo = wset;                 // windows k_pool_eval has to evaluate
@@ -1163,11 +1202,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_frontier_all(FrontAllP
                 fl[i] = f;
                 N[i] = todo;
                 front[i] = wset;
-                uint32_t z = nz[i];
                 if (wset) { z = (z & ~wset) | (wset & window_or(bufB, i)); nz[i] = z; }
                 Z[i] = z;
                 Hd[i] = wset;                         // Hd is free in the pool branch: the layer's output events for the next layer
-            }
+            });
             __syncthreads();
             emit_sites(N, L.H, L.Ww, (uint32_t)s << L.code.sh_s, L.code.sh_y, L.sites, L.counter, scratch);
             __syncthreads();
